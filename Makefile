@@ -1,0 +1,39 @@
+# cuSten-B200 build: sm_100a only.
+#   make lib      -> custen_b200/lib/libcuSten.a        (relocatable device code, the reference's library form)
+#                    custen_b200/lib/libcusten_b200.so   (C ABI, device-linked, for FFI users and the tests)
+#   make oracle   -> oracle/_ref/*                       (CPU oracle + the reference rebuilt from /root/reference)
+NVCC      ?= nvcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -rdc=true -Xcompiler -fPIC -Xcompiler -fvisibility=default
+SRCDIR    := custen_b200/csrc
+OBJDIR    := build/obj
+LIBDIR    := custen_b200/lib
+
+CORE_SRC  := kernels.cu plan.cu api_cpp.cu
+CABI_SRC  := api_c.cu
+CORE_OBJ  := $(patsubst %.cu,$(OBJDIR)/%.o,$(CORE_SRC))
+CABI_OBJ  := $(patsubst %.cu,$(OBJDIR)/%.o,$(CABI_SRC))
+HEADERS   := $(wildcard $(SRCDIR)/*.h $(SRCDIR)/*.cuh include/*.h)
+
+.PHONY: all lib oracle clean
+all: lib oracle
+
+lib: $(LIBDIR)/libcuSten.a $(LIBDIR)/libcusten_b200.so
+
+$(OBJDIR)/%.o: $(SRCDIR)/%.cu $(HEADERS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -c -o $@ $<
+
+$(LIBDIR)/libcuSten.a: $(CORE_OBJ)
+	@mkdir -p $(LIBDIR)
+	$(NVCC) --lib $(CORE_OBJ) --output-file $@
+
+$(LIBDIR)/libcusten_b200.so: $(CORE_OBJ) $(CABI_OBJ)
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(ARCH) -shared -o $@ $(CORE_OBJ) $(CABI_OBJ)
+
+oracle:
+	$(MAKE) -C oracle
+
+clean:
+	rm -rf build $(LIBDIR) oracle/_ref

@@ -1,0 +1,428 @@
+#!/usr/bin/env python
+"""cuSten-B200 benchmark: 2D stencil Gpoints/s and HBM GB/s (BASELINE.json `metric`).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+Default workload (every N): BASELINE.json configs[3], the 2D XY periodic function-pointer stencil (nonlinear
+c^3 - c term through a 3x3 Laplacian, cuPentCahnADI.cu:164-188) on a 32768^2 FP64 grid — the configuration the
+multi-GPU target is quoted on; it fits one B200 (2 x 8 GiB), so N = 1 runs the same grid and the scaling is strong.
+A step is one sweep of the whole grid: at N > 1 each rank owns a y-slab and a step is halo transport + sweep.
+At N = 1 the line also carries a per-variant table on 16384^2 (the single-GPU target size) and the configs[1] /
+configs[2] workloads.
+
+`value` is timed with inputs resident in HBM; `e2e` goes through the same C ABI with the grid in pinned HOST
+memory (the numTiles out-of-core path: H2D of every tile and D2H of every result inside the timed region).
+--impl reference times the reference's own CPU implementation of this path (serialCahnADI.c nonlinearRHS,
+compiled from /root/reference into oracle/_ref/) on the host cores.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+METRIC = "2d_stencil_gpoints_per_s"
+UNIT = "Gpoints/s"
+ALG_BYTES_PER_POINT = 16.0  # one FP64 read + one FP64 write per grid point per sweep
+
+WORKLOADS = {
+    # name: (variant, n, tiles, description)
+    "xy_p_fun_32768": ("XYpFun", 32768, 1, "configs[3]: 2D XY periodic Fun stencil (c^3-c, 3x3), 32768^2 FP64"),
+    "x_p_8192": ("Xp", 8192, 1, "configs[1]: 2D X periodic 9-pt 8th-order d2/dx2 (2d_x_p example), 8192^2 FP64"),
+    "xy_np_16384_t4": ("XYnp", 16384, 4, "configs[2]: 2D XY non-periodic 3x3 cross stencil, 16384^2 FP64, numTiles=4"),
+    "xy_p_fun_16384": ("XYpFun", 16384, 1, "2D XY periodic Fun stencil (c^3-c, 3x3), 16384^2 FP64"),
+}
+
+
+def stencil_args(variant, n):
+    """Coefficients / window of the named workloads (SURVEY.md section 8d 'synthetic inputs')."""
+    import cases
+    h = 2 * np.pi / n
+    d = "XY" if variant.startswith("XY") else variant[0]
+    fun = None
+    if d == "X":
+        coef, kw = cases.weights_d2_8th(h), dict(H=9, L=4, R=4)
+        if variant.endswith("Fun"):
+            fun, kw["numCoe"] = "weighted9_x", 9
+    elif d == "Y":
+        coef, kw = cases.weights_d2_8th(h), dict(V=9, T=4, B=4)
+        if variant.endswith("Fun"):
+            fun = "weighted9_y"
+            if variant == "YpFun":
+                kw["numCoe"] = 9
+    elif variant.endswith("Fun"):
+        # sigma_N * 5-point Laplacian applied to c^3 - c (cuPentCahnADI.cu:496-516), dt = 0.1 dx, D = 1
+        dx = 16 * np.pi / n
+        coef, kw, fun = cases.weights_laplace5((0.1 * dx / 3.0) * 2.0 / dx ** 2), dict(H=3, L=1, R=1, V=3, T=1, B=1), "cubic_xy"
+    else:
+        coef, kw = cases.weights_cross_xy(h, h), dict(H=3, L=1, R=1, V=3, T=1, B=1)
+    kw["fun"] = fun
+    return coef, kw
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.th.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's serial CPU code (oracle/_ref/libserialcahn.so)
+# ------------------------------------------------------------------------------------------------------------
+
+def _serial_lib():
+    import oracle_lib as ol
+    lib = ol.serial()
+    if lib is None:
+        raise RuntimeError("oracle/_ref/libserialcahn.so not available")
+    return lib
+
+
+def cpu_sweeps(n, threads, repeats):
+    """`threads` host threads, each sweeping its own n x n field `repeats` times with the reference's
+    nonlinearRHS (serialCahnADI.c:553-622).  Returns seconds for the whole batch."""
+    lib = _serial_lib()
+    _dp = ctypes.POINTER(ctypes.c_double)
+    import cases
+    dx = 16 * np.pi / n
+    w = np.ascontiguousarray(cases.weights_laplace5((0.1 * dx / 3.0) * 2.0 / dx ** 2))
+    rng = np.random.default_rng(1)
+    bufs = [(np.ascontiguousarray(rng.uniform(-0.1, 0.1, (n, n))), np.zeros((n, n))) for _ in range(threads)]
+
+    def work(i):
+        a, b = bufs[i]
+        for _ in range(repeats):
+            lib.nonlinearRHS(a.ctypes.data_as(_dp), b.ctypes.data_as(_dp), w.ctypes.data_as(_dp), 3, 3, 1, 1, n)
+
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    t0 = time.perf_counter()
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    return time.perf_counter() - t0
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0))
+    n = 2048
+    for _ in range(args.warmup):
+        cpu_sweeps(n, cores, 1)
+    t = cpu_sweeps(n, cores, args.steps)
+    value = cores * n * n * args.steps / t / 1e9
+    variant, size, tiles, desc = WORKLOADS[args.workload]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "description": desc,
+                   "note": "reference CPU implementation of the path: serialCahnADI.c nonlinearRHS (3x3 c^3-c stencil, periodic)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
+                         "sample": f"{cores} threads x {args.steps} sweeps of an independent {n}^2 periodic field each"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------
+
+def time_resident(cs, st, steps, warmup, pre_step=None):
+    """Median-free contract timing: W warm-ups, then exactly K steps between two events on the launching stream."""
+    lib = cs.load()
+    h = ctypes.addressof(st.handle)
+    for _ in range(warmup):
+        if pre_step:
+            pre_step()
+        st.compute(cs.DEVICE)
+    cs.device_synchronize()
+    e0, e1 = lib.custen_event_create(), lib.custen_event_create()
+    time_resident.launches = -cs.launch_count()
+    lib.custen_event_record(e0, h, 0)
+    for _ in range(steps):
+        if pre_step:
+            pre_step()
+        st.compute(cs.DEVICE)
+    lib.custen_event_record(e1, h, 0)
+    lib.custen_event_synchronize(e1)
+    time_resident.launches += cs.launch_count()
+    ms = lib.custen_event_elapsed_ms(e0, e1)
+    lib.custen_event_destroy(e0)
+    lib.custen_event_destroy(e1)
+    return ms
+
+
+def variant_table(cs, torch, n, steps, warmup, peak):
+    """All 12 variants on an n x n grid, device-resident (the '>= 80 % of HBM peak on 16384^2' target)."""
+    table = {}
+    inp = (torch.rand((n, n), device="cuda", dtype=torch.float64) * 0.2 - 0.1)
+    out = torch.zeros_like(inp)
+    for v in cs.VARIANTS:
+        coef, kw = stencil_args(v, n)
+        tc = torch.from_numpy(np.ascontiguousarray(coef)).cuda()
+        st = cs.Stencil2D(v, n, n, out, inp, tc, **kw)
+        ms = time_resident(cs, st, steps, warmup) / steps
+        gpts = n * n / ms / 1e6
+        table[v] = {"gpoints_per_s": round(gpts, 2), "hbm_gbs": round(gpts * ALG_BYTES_PER_POINT, 1),
+                    "frac_of_peak": round(gpts * ALG_BYTES_PER_POINT / peak, 4), "path": st.path}
+        st.destroy()
+    return table
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import custen_b200 as cs
+    import custen_b200.slab as slab
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    variant, n, tiles, desc = WORKLOADS[args.workload]
+    coef, kw = stencil_args(variant, n)
+    rows = n // world
+    peak, peak_src = peaks()
+
+    gen = torch.Generator(device="cuda").manual_seed(0x5EED + rank)
+    inp = torch.rand((rows, n), generator=gen, device="cuda", dtype=torch.float64) * 0.2 - 0.1
+    out = torch.zeros_like(inp)
+    tcoef = torch.from_numpy(np.ascontiguousarray(coef)).cuda()
+
+    # ---- resident timing ----------------------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if world == 1:
+        st = cs.Stencil2D(variant, n, n, out, inp, tcoef, numTiles=tiles, deviceNum=local_rank, **kw)
+        ms = time_resident(cs, st, args.steps, args.warmup)
+        path = st.path
+        launches_timed = time_resident.launches
+        st.destroy()
+    else:
+        ss = slab.SlabStencil(variant, n, n, inp, out, tcoef, transport=args.transport, numTiles=tiles, **kw)
+        for _ in range(args.warmup):
+            ss.step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = cs.launch_count()
+        e0.record()
+        for _ in range(args.steps):
+            ss.step()
+        e1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        launches_timed = cs.launch_count() - l0
+        t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        path = ss.st.path
+        ss.destroy()
+    clocks = sampler.stop()
+    ms_per_step = ms / args.steps
+    value = n * n / ms_per_step / 1e6  # Gpoints/s, whole job
+
+    # ---- end to end: grid in pinned host memory, through the out-of-core tile scheduler -----------------------
+    e2e = None
+    if not args.no_e2e:
+        lib = cs.load()
+        nbytes = rows * n * 8
+        h_in, h_out = lib.custen_host_alloc(nbytes), lib.custen_host_alloc(nbytes)
+        v_in = np.ctypeslib.as_array((ctypes.c_double * (rows * n)).from_address(h_in))
+        torch.from_numpy(v_in).copy_(inp.view(-1).cpu())
+        e2e_tiles = max(tiles, args.e2e_tiles)
+        st = cs.Stencil2D(variant, n, rows, h_out, h_in, tcoef, numTiles=e2e_tiles, deviceNum=local_rank, **kw)
+        halo_bytes = 0
+        if world > 1 and not variant.startswith("Xp") and not variant.startswith("Xnp"):
+            T, B = kw.get("T", 0), kw.get("B", 0)
+            top = torch.empty((max(T, 1), n), device="cuda", dtype=torch.float64)
+            bot = torch.empty((max(B, 1), n), device="cuda", dtype=torch.float64)
+            periodic = not variant.replace("Fun", "").endswith("np")
+            st.set_slab(top, bot, rank == 0, rank == world - 1)
+            h_view = torch.from_numpy(v_in).view(rows, n)
+            halo_bytes = (T + B) * n * 8
+
+            def pre():
+                # edge rows of the host-resident slab travel H2D, then over NVLink to the neighbours
+                first_rows = h_view[:max(B, 1)].cuda(non_blocking=True)
+                last_rows = h_view[-max(T, 1):].cuda(non_blocking=True)
+                # exchange_halos only touches local[:B] and local[-T:], so a two-piece stand-in is enough
+                standin = torch.cat([first_rows, last_rows])
+                slab.exchange_halos(standin, T, B, top[:T], bot[:B], rank, world, periodic)
+        else:
+            pre = None
+
+        def e2e_step():
+            if pre:
+                pre()
+            st.compute(cs.HOST)
+
+        for _ in range(max(1, min(args.warmup, 2))):
+            e2e_step()
+        cs.device_synchronize()
+        if dist:
+            dist.barrier()
+        k = max(1, min(args.steps, args.e2e_steps))
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(k):
+            e2e_step()
+        t1.record()
+        torch.cuda.synchronize()
+        tt = torch.tensor([t0.elapsed_time(t1)], device="cuda", dtype=torch.float64)
+        if dist:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tt.item()) / k
+        e2e = {"value": n * n / e2e_ms / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(world * (nbytes + halo_bytes)),
+               "d2h_bytes_per_step": int(world * nbytes), "ms_per_step": e2e_ms, "steps": k, "numTiles": e2e_tiles,
+               "path": "custenCompute2D%s(HOST) on pinned host buffers: staged tile pipeline" % variant}
+        st.destroy()
+        cs.device_synchronize()
+        lib.custen_host_free(h_in)
+        lib.custen_host_free(h_out)
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+
+    # ---- rank 0 extras: per-variant table, other configs, cpu baseline -----------------------------------------
+    del inp, out
+    torch.cuda.empty_cache()
+    extras = {}
+    if world == 1 and not args.no_table:
+        extras["variants_16384"] = variant_table(cs, torch, 16384, 10, 3, peak)
+        for wname in ("x_p_8192", "xy_np_16384_t4"):
+            v2, n2, t2, d2 = WORKLOADS[wname]
+            c2, k2 = stencil_args(v2, n2)
+            a = torch.rand((n2, n2), device="cuda", dtype=torch.float64)
+            b = torch.zeros_like(a)
+            s2 = cs.Stencil2D(v2, n2, n2, b, a, torch.from_numpy(np.ascontiguousarray(c2)).cuda(), numTiles=t2, **k2)
+            m2 = time_resident(cs, s2, 20, 3) / 20
+            extras[wname] = {"gpoints_per_s": round(n2 * n2 / m2 / 1e6, 2),
+                             "frac_of_peak": round(n2 * n2 * ALG_BYTES_PER_POINT / m2 / 1e6 / peak, 4), "path": s2.path}
+            s2.destroy()
+            del a, b
+
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        try:
+            ncpu, reps = 4096, 0
+            t = 0.0
+            while t < 10.0 and reps < 64:
+                t += cpu_sweeps(ncpu, 1, 1)
+                reps += 1
+            cpu = {"value": ncpu * ncpu * reps / t / 1e9, "unit": UNIT, "cores": 1, "kind": "reference",
+                   "sample": f"{reps} sweeps of a {ncpu}^2 periodic field by the reference's serial nonlinearRHS "
+                             f"(serialCahnADI.c:553-622), {t:.1f} s on 1 of {len(os.sched_getaffinity(0))} host threads"}
+        except Exception as ex:  # the oracle is a checker; its absence must not hide the GPU numbers
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"unavailable: {ex}"}
+
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(args.workload if world == 1 else "", None)
+    achieved = value / world * ALG_BYTES_PER_POINT  # GB/s per GPU
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "description": desc, "grid": [n, n], "rows_per_gpu": rows,
+                   "numTiles": tiles, "parallelism": f"y-slabs x{world}" + (f", halo transport: {args.transport}" if world > 1 else ""),
+                   "l2": "no flush: every sweep streams 2 x %.1f GiB per GPU, far larger than the 126 MB L2" % (rows * n * 8 / 2 ** 30),
+                   "kernel_family": path},
+        "clocks": clocks,
+        "e2e": e2e,
+        "gpu_launches": int(launches_timed),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src,
+                     "note": "algorithmic 16 B/point x points per launch / mean launch duration (CUDA events on the "
+                             "launching stream over the timed region); per GPU"},
+        "cpu_baseline": cpu,
+    }
+    line.update(extras)
+    print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="xy_p_fun_32768", choices=sorted(WORKLOADS))
+    ap.add_argument("--transport", default="exchange", choices=["exchange", "peer"])
+    ap.add_argument("--e2e-tiles", type=int, default=8)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-table", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus:
+        if args.gpus > 1 and world == 1:
+            # convenience: re-launch under torchrun
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
+            sys.exit(subprocess.call(cmd))
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

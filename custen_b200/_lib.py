@@ -1,0 +1,86 @@
+"""ctypes loader for libcusten_b200.so (the C ABI declared in include/custen_c.h).
+
+There is no CPU fallback: if the CUDA library has not been built, or cannot be loaded, importing the
+API raises.  Build it with `make lib` (or `python -c "import __graft_entry__ as g; g.build()"`).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libcusten_b200.so")
+
+VARIANTS = ("Xp", "Xnp", "XpFun", "XnpFun", "Yp", "Ynp", "YpFun", "YnpFun", "XYp", "XYnp", "XYpFun", "XYnpFun")
+
+_c_int, _c_dbl_p, _c_void_p = ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p
+_PREFIX = [_c_void_p] + [_c_int] * 6 + [_c_dbl_p, _c_dbl_p]
+
+# trailing Create parameters after dataInput, per variant (include/custen_c.h)
+_CREATE_TAIL = {
+    "Xp": [_c_dbl_p, _c_int, _c_int, _c_int],
+    "Xnp": [_c_dbl_p, _c_int, _c_int, _c_int],
+    "XpFun": [_c_dbl_p, _c_int, _c_int, _c_int, _c_int, _c_dbl_p],
+    "XnpFun": [_c_dbl_p, _c_int, _c_int, _c_int, _c_int, _c_dbl_p],
+    "Yp": [_c_dbl_p, _c_int, _c_int, _c_int],
+    "Ynp": [_c_dbl_p, _c_int, _c_int, _c_int],
+    "YpFun": [_c_dbl_p, _c_int, _c_int, _c_int, _c_int, _c_dbl_p],
+    "YnpFun": [_c_dbl_p, _c_int, _c_int, _c_int, _c_dbl_p],
+    "XYp": [_c_dbl_p] + [_c_int] * 6,
+    "XYnp": [_c_dbl_p] + [_c_int] * 6,
+    "XYpFun": [_c_dbl_p] + [_c_int] * 6 + [_c_dbl_p],
+    "XYnpFun": [_c_dbl_p] + [_c_int] * 6 + [_c_dbl_p],
+}
+
+# every symbol include/custen_c.h declares (tests check the library exports all of them)
+EXPORTED = (
+    [f"custen{op}2D{v}" for v in VARIANTS for op in ("Create", "Swap", "Destroy", "Compute")]
+    + ["custenCheckError", "custen_handle_size", "custen_device_synchronize", "custen_builtin_fun",
+       "custen_last_path", "custen_last_mode", "custen_launch_count", "custen_set_tuning", "custen_set_slab",
+       "custen_ipc_export", "custen_ipc_open", "custen_ipc_close", "custen_event_create", "custen_event_record",
+       "custen_event_synchronize", "custen_event_elapsed_ms", "custen_event_destroy", "custen_host_alloc",
+       "custen_host_free", "custen_managed_alloc", "custen_managed_free"]
+)
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library (once) and declare the prototypes.  Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: cuSten-B200 has no CPU fallback; build the CUDA library with `make lib`")
+    lib = ctypes.CDLL(LIB_PATH)
+    for v in VARIANTS:
+        f = getattr(lib, f"custenCreate2D{v}")
+        f.argtypes, f.restype = _PREFIX + _CREATE_TAIL[v], None
+        f = getattr(lib, f"custenSwap2D{v}")
+        f.argtypes, f.restype = [_c_void_p, _c_dbl_p], None
+        f = getattr(lib, f"custenDestroy2D{v}")
+        f.argtypes, f.restype = [_c_void_p], None
+        f = getattr(lib, f"custenCompute2D{v}")
+        f.argtypes, f.restype = [_c_void_p, _c_int], None
+    lib.custenCheckError.argtypes, lib.custenCheckError.restype = [ctypes.c_char_p], None
+    lib.custen_handle_size.argtypes, lib.custen_handle_size.restype = [], ctypes.c_size_t
+    lib.custen_device_synchronize.argtypes, lib.custen_device_synchronize.restype = [], None
+    lib.custen_builtin_fun.argtypes, lib.custen_builtin_fun.restype = [ctypes.c_char_p], ctypes.c_void_p
+    lib.custen_last_path.argtypes, lib.custen_last_path.restype = [_c_void_p], _c_int
+    lib.custen_last_mode.argtypes, lib.custen_last_mode.restype = [_c_void_p], _c_int
+    lib.custen_launch_count.argtypes, lib.custen_launch_count.restype = [], ctypes.c_uint64
+    lib.custen_set_tuning.argtypes, lib.custen_set_tuning.restype = [_c_int] * 4, None
+    lib.custen_set_slab.argtypes, lib.custen_set_slab.restype = [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int], None
+    lib.custen_ipc_export.argtypes, lib.custen_ipc_export.restype = [_c_void_p, _c_void_p, _c_void_p], None
+    lib.custen_ipc_open.argtypes, lib.custen_ipc_open.restype = [_c_void_p], ctypes.c_void_p
+    lib.custen_ipc_close.argtypes, lib.custen_ipc_close.restype = [_c_void_p], None
+    lib.custen_event_create.argtypes, lib.custen_event_create.restype = [], ctypes.c_void_p
+    lib.custen_event_record.argtypes, lib.custen_event_record.restype = [_c_void_p, _c_void_p, _c_int], None
+    lib.custen_event_synchronize.argtypes, lib.custen_event_synchronize.restype = [_c_void_p], None
+    lib.custen_event_elapsed_ms.argtypes, lib.custen_event_elapsed_ms.restype = [_c_void_p, _c_void_p], ctypes.c_float
+    lib.custen_event_destroy.argtypes, lib.custen_event_destroy.restype = [_c_void_p], None
+    lib.custen_host_alloc.argtypes, lib.custen_host_alloc.restype = [ctypes.c_size_t], ctypes.c_void_p
+    lib.custen_host_free.argtypes, lib.custen_host_free.restype = [_c_void_p], None
+    lib.custen_managed_alloc.argtypes, lib.custen_managed_alloc.restype = [ctypes.c_size_t], ctypes.c_void_p
+    lib.custen_managed_free.argtypes, lib.custen_managed_free.restype = [_c_void_p], None
+    _lib = lib
+    return lib

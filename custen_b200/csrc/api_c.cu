@@ -1,0 +1,207 @@
+// extern "C" boundary of libcusten_b200.so (declared in include/custen_c.h).
+#include "../../include/custen_c.h"
+#include "builtin_funs.cuh"
+#include "plan.h"
+
+#include <cstring>
+
+using namespace custen;
+
+static inline cuSten_t* H(cuSten_c_handle* h) { return reinterpret_cast<cuSten_t*>(h); }
+
+// ---- user-function fixtures: device-side pointer variables, read back like a C++ caller would -----------------
+__device__ cuStenFunX fp_second_diff_x = custen_funs::second_diff_x;
+__device__ cuStenFunX fp_weighted9_x = custen_funs::weighted9_x;
+__device__ cuStenFunY fp_weighted9_y = custen_funs::weighted9_y;
+__device__ cuStenFunY fp_weighted3_y = custen_funs::weighted3_y;
+__device__ cuStenFunXY fp_weighted_xy = custen_funs::weighted_xy;
+__device__ cuStenFunXY fp_cubic_xy = custen_funs::cubic_xy;
+
+extern "C" {
+
+#define C_COMMON(V)                                                                                        \
+    void custenSwap2D##V(cuSten_c_handle* h, double* dataInput) { cuStenSwap2D##V(H(h), dataInput); }       \
+    void custenDestroy2D##V(cuSten_c_handle* h) { cuStenDestroy2D##V(H(h)); }                               \
+    void custenCompute2D##V(cuSten_c_handle* h, int offload) { cuStenCompute2D##V(H(h), offload != 0); }
+
+#define PFX cuSten_c_handle *h, int dev, int tiles, int nx, int ny, int bx, int by, double *out, double *in
+#define PFA H(h), dev, tiles, nx, ny, bx, by, out, in
+
+void custenCreate2DXp(PFX, double* w, int n, int l, int r) { cuStenCreate2DXp(PFA, w, n, l, r); }
+C_COMMON(Xp)
+void custenCreate2DXnp(PFX, double* w, int n, int l, int r) { cuStenCreate2DXnp(PFA, w, n, l, r); }
+C_COMMON(Xnp)
+void custenCreate2DXpFun(PFX, double* c, int n, int l, int r, int nc, double* f) { cuStenCreate2DXpFun(PFA, c, n, l, r, nc, f); }
+C_COMMON(XpFun)
+void custenCreate2DXnpFun(PFX, double* c, int n, int l, int r, int nc, double* f) { cuStenCreate2DXnpFun(PFA, c, n, l, r, nc, f); }
+C_COMMON(XnpFun)
+
+void custenCreate2DYp(PFX, double* w, int n, int t, int b) { cuStenCreate2DYp(PFA, w, n, t, b); }
+C_COMMON(Yp)
+void custenCreate2DYnp(PFX, double* w, int n, int t, int b) { cuStenCreate2DYnp(PFA, w, n, t, b); }
+C_COMMON(Ynp)
+void custenCreate2DYpFun(PFX, double* c, int n, int t, int b, int nc, double* f) { cuStenCreate2DYpFun(PFA, c, n, t, b, nc, f); }
+C_COMMON(YpFun)
+void custenCreate2DYnpFun(PFX, double* c, int n, int t, int b, double* f) { cuStenCreate2DYnpFun(PFA, c, n, t, b, f); }
+C_COMMON(YnpFun)
+
+void custenCreate2DXYp(PFX, double* w, int hh, int l, int r, int vv, int t, int b) { cuStenCreate2DXYp(PFA, w, hh, l, r, vv, t, b); }
+C_COMMON(XYp)
+void custenCreate2DXYnp(PFX, double* w, int hh, int l, int r, int vv, int t, int b) { cuStenCreate2DXYnp(PFA, w, hh, l, r, vv, t, b); }
+C_COMMON(XYnp)
+void custenCreate2DXYpFun(PFX, double* c, int hh, int l, int r, int vv, int t, int b, double* f)
+{
+    cuStenCreate2DXYpFun(PFA, c, hh, l, r, vv, t, b, f);
+}
+C_COMMON(XYpFun)
+void custenCreate2DXYnpFun(PFX, double* c, int hh, int l, int r, int vv, int t, int b, double* f)
+{
+    cuStenCreate2DXYnpFun(PFA, c, hh, l, r, vv, t, b, f);
+}
+C_COMMON(XYnpFun)
+
+void custenCheckError(const char* action) { checkError(action); }
+
+// ---- additive -------------------------------------------------------------------------------------------------
+
+size_t custen_handle_size(void) { return sizeof(cuSten_t); }
+
+void custen_device_synchronize(void)
+{
+    cudaDeviceSynchronize();
+    checkError("cudaDeviceSynchronize");
+}
+
+double* custen_builtin_fun(const char* name)
+{
+    void* fp = nullptr;
+#define LOOKUP(N)                                                     \
+    if (!strcmp(name, #N))                                            \
+    {                                                                 \
+        cudaMemcpyFromSymbol(&fp, fp_##N, sizeof(void*));             \
+        checkError("reading device function pointer " #N);            \
+        return (double*)fp;                                           \
+    }
+    LOOKUP(second_diff_x)
+    LOOKUP(weighted9_x)
+    LOOKUP(weighted9_y)
+    LOOKUP(weighted3_y)
+    LOOKUP(weighted_xy)
+    LOOKUP(cubic_xy)
+#undef LOOKUP
+    return nullptr;
+}
+
+int custen_last_path(cuSten_c_handle* h)
+{
+    Plan* p = plan_of(H(h));
+    return p ? p->last_path : -1;
+}
+int custen_last_mode(cuSten_c_handle* h)
+{
+    Plan* p = plan_of(H(h));
+    return p ? p->last_mode : -1;
+}
+uint64_t custen_launch_count(void) { return launches_total(); }
+
+void custen_set_tuning(int force_fallback, int force_tile, int chunk_rows, int ctas_per_sm)
+{
+    Tuning& t = tuning();
+    t.force_fallback = force_fallback;
+    t.force_tile = force_tile;
+    t.chunk_rows = chunk_rows;
+    t.ctas_per_sm = ctas_per_sm;
+}
+
+void custen_set_slab(cuSten_c_handle* h, const double* top, const double* bottom, int is_first, int is_last)
+{
+    Plan* p = plan_of(H(h));
+    if (!p) return;
+    p->slab_enabled = 1;
+    p->slab_top = top;
+    p->slab_bottom = bottom;
+    p->slab_first = is_first;
+    p->slab_last = is_last;
+}
+
+void custen_ipc_export(const void* dev_ptr, void* handle64, size_t* offset_out)
+{
+    cudaIpcMemHandle_t hd;
+    cudaIpcGetMemHandle(&hd, const_cast<void*>(dev_ptr));
+    checkError("cudaIpcGetMemHandle");
+    memcpy(handle64, &hd, sizeof hd);
+    // base of the allocation, through the driver entry point (no link-time dependency on libcuda)
+    size_t off = 0;
+    typedef int (*GetRange)(unsigned long long*, size_t*, unsigned long long);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr) == cudaSuccess && fn)
+    {
+        unsigned long long base = 0;
+        size_t size = 0;
+        if (((GetRange)fn)(&base, &size, (unsigned long long)(uintptr_t)dev_ptr) == 0)
+            off = (size_t)((uintptr_t)dev_ptr - (uintptr_t)base);
+    }
+    cudaGetLastError();
+    if (offset_out) *offset_out = off;
+}
+void* custen_ipc_open(const void* handle64)
+{
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handle64, sizeof hd);
+    void* p = nullptr;
+    cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess);
+    checkError("cudaIpcOpenMemHandle");
+    return p;
+}
+void custen_ipc_close(void* mapped_ptr)
+{
+    cudaIpcCloseMemHandle(mapped_ptr);
+    checkError("cudaIpcCloseMemHandle");
+}
+
+void* custen_event_create(void)
+{
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    checkError("cudaEventCreate");
+    return e;
+}
+void custen_event_record(void* ev, cuSten_c_handle* h, int stream_idx)
+{
+    cudaEventRecord((cudaEvent_t)ev, H(h)->streams[stream_idx]);
+    checkError("cudaEventRecord");
+}
+void custen_event_synchronize(void* ev)
+{
+    cudaEventSynchronize((cudaEvent_t)ev);
+    checkError("cudaEventSynchronize");
+}
+float custen_event_elapsed_ms(void* start, void* stop)
+{
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, (cudaEvent_t)start, (cudaEvent_t)stop);
+    checkError("cudaEventElapsedTime");
+    return ms;
+}
+void custen_event_destroy(void* ev) { cudaEventDestroy((cudaEvent_t)ev); }
+
+void* custen_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
+    checkError("cudaHostAlloc");
+    return p;
+}
+void custen_host_free(void* p) { cudaFreeHost(p); }
+
+void* custen_managed_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    cudaMallocManaged(&p, bytes);
+    checkError("cudaMallocManaged");
+    return p;
+}
+void custen_managed_free(void* p) { cudaFree(p); }
+
+}  // extern "C"

@@ -1,0 +1,492 @@
+// Plan builder + tile scheduler (host side).  See plan.h for the reference locations re-created here.
+#include "plan.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <utility>
+
+namespace custen {
+
+static const uintptr_t kMagic = 0xC0573B200C0573ull;
+
+static void check(const char* what, int device)
+{
+    char msg[256];
+    snprintf(msg, sizeof msg, "%s on GPU %d", what, device);
+    checkError(msg);
+}
+
+Plan* plan_of(cuSten_t* h)
+{
+    if (!h || !h->streams) return nullptr;
+    uintptr_t* tail = reinterpret_cast<uintptr_t*>(h->streams + 3);
+    if (tail[0] != kMagic) return nullptr;
+    return reinterpret_cast<Plan*>(tail[1]);
+}
+
+MemKind classify(const void* p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return MK_HOST;
+    }
+    if (at.type == cudaMemoryTypeManaged) return MK_MANAGED;
+    if (at.type == cudaMemoryTypeDevice) return MK_DEVICE;
+    return MK_HOST;  // registered / pinned or plain pageable host memory
+}
+
+// Tile seam pointers.  Same values the reference computes (custenCreateDestroy2DXYp.cu:194-228):
+// the T rows above tile t and the B rows below it, taken from the same array, wrapped at the ends.
+static void set_boundaries(cuSten_t* h, double* base)
+{
+    const int n = h->numTiles;
+    const ptrdiff_t nx = h->nx;
+    for (int t = 0; t < n; ++t)
+    {
+        h->boundaryTop[t] = (t == 0) ? base + (ptrdiff_t)(h->ny - h->numStenTop) * nx
+                                     : base + ((ptrdiff_t)h->nyTile * t - h->numStenTop) * nx;
+        h->boundaryBottom[t] = (t == n - 1) ? base : base + (ptrdiff_t)h->nyTile * (t + 1) * nx;
+    }
+}
+
+void plan_create(cuSten_t* h, Spec spec, int deviceNum, int numTiles, int nx, int ny, int BLOCK_X, int BLOCK_Y,
+                 double* dataOutput, double* dataInput, double* coef, int H, int L, int R, int V, int T, int B,
+                 int numCoe, double* func)
+{
+    memset(h, 0, sizeof *h);
+    h->deviceNum = deviceNum;
+    h->numStreams = 3;
+    h->numTiles = numTiles < 1 ? 1 : numTiles;
+    h->nx = nx;
+    h->ny = ny;
+    h->BLOCK_X = BLOCK_X;
+    h->BLOCK_Y = BLOCK_Y;
+
+    cudaSetDevice(deviceNum);
+    check("Setting current device", deviceNum);
+
+    // three public streams (blocking, like the reference's cudaStreamCreate) + hidden tail
+    h->streams = (cudaStream_t*)calloc(3 + 2, sizeof(cudaStream_t));
+    for (int s = 0; s < 3; ++s)
+    {
+        cudaStreamCreate(&h->streams[s]);
+        check("Creating stream", deviceNum);
+    }
+    h->events = (cudaEvent_t*)calloc(2, sizeof(cudaEvent_t));
+    for (int e = 0; e < 2; ++e)
+    {
+        cudaEventCreateWithFlags(&h->events[e], cudaEventDisableTiming);
+        check("Creating event", deviceNum);
+    }
+
+    Plan* p = (Plan*)calloc(1, sizeof(Plan));
+    p->spec = spec;
+    uintptr_t* tail = reinterpret_cast<uintptr_t*>(h->streams + 3);
+    tail[0] = kMagic;
+    tail[1] = reinterpret_cast<uintptr_t>(p);
+
+    // public geometry fields, as the reference fills them
+    h->numStenLeft = L;
+    h->numStenRight = R;
+    h->numStenTop = T;
+    h->numStenBottom = B;
+    h->numStenHoriz = H;
+    h->numStenVert = V;
+    h->numSten = H * V;
+    h->nxLocal = BLOCK_X + L + R;
+    h->nyLocal = BLOCK_Y + T + B;
+    if (spec.fun)
+    {
+        h->coe = coef;
+        h->numCoe = numCoe;
+        h->devFunc = func;
+        p->ncoef = numCoe;
+    }
+    else
+    {
+        h->weights = coef;
+        p->ncoef = H * V;
+    }
+    h->mem_shared = (int)(((size_t)h->nxLocal * h->nyLocal + p->ncoef) * sizeof(double));
+    h->nyTile = ny / h->numTiles;
+    h->xGrid = BLOCK_X > 0 ? (nx + BLOCK_X - 1) / BLOCK_X : 0;
+    h->yGrid = BLOCK_Y > 0 ? (h->nyTile + BLOCK_Y - 1) / BLOCK_Y : 0;
+
+    h->dataInput = (double**)calloc(h->numTiles, sizeof(double*));
+    h->dataOutput = (double**)calloc(h->numTiles, sizeof(double*));
+    const ptrdiff_t off = (ptrdiff_t)nx * h->nyTile;
+    for (int t = 0; t < h->numTiles; ++t)
+    {
+        h->dataInput[t] = dataInput + t * off;
+        h->dataOutput[t] = dataOutput + t * off;
+    }
+    if (spec.dir != DIR_X)
+    {
+        h->boundaryTop = (double**)calloc(h->numTiles, sizeof(double*));
+        h->boundaryBottom = (double**)calloc(h->numTiles, sizeof(double*));
+        set_boundaries(h, dataInput);
+        h->numBoundaryTop = T * nx;
+        h->numBoundaryBottom = B * nx;
+    }
+}
+
+void plan_swap(cuSten_t* h, double* dataInput)
+{
+    for (int t = 0; t < h->numTiles; ++t) std::swap(h->dataInput[t], h->dataOutput[t]);
+    // Y / XY variants re-derive the seams from the array that becomes the next input
+    // (custenCreateDestroy2DXYp.cu:253-310); X variants ignore the argument (…2DXp.cu:179-190).
+    if (h->boundaryTop && dataInput) set_boundaries(h, dataInput);
+}
+
+static void release_staging(Plan* p)
+{
+    for (int s = 0; s < kSlots; ++s)
+    {
+        if (p->d_in[s]) cudaFree(p->d_in[s]);
+        if (p->d_out[s]) cudaFree(p->d_out[s]);
+        p->d_in[s] = p->d_out[s] = nullptr;
+        if (p->events_ready)
+        {
+            cudaEventDestroy(p->ev_loaded[s]);
+            cudaEventDestroy(p->ev_done[s]);
+            cudaEventDestroy(p->ev_unloaded[s]);
+        }
+    }
+    if (p->d_coef) cudaFree(p->d_coef);
+    p->d_coef = nullptr;
+    p->events_ready = 0;
+    p->stage_rows = 0;
+}
+
+void plan_destroy(cuSten_t* h)
+{
+    cudaSetDevice(h->deviceNum);
+    check("Setting current device", h->deviceNum);
+    Plan* p = plan_of(h);
+    if (p)
+    {
+        // staging buffers may still be in flight: drain this handle's streams before freeing them
+        if (p->stage_rows || p->d_coef)
+            for (int s = 0; s < 3; ++s) cudaStreamSynchronize(h->streams[s]);
+        release_staging(p);
+        free(p);
+    }
+    for (int s = 0; s < h->numStreams && s < 3; ++s)
+    {
+        cudaStreamDestroy(h->streams[s]);
+        check("Destroying stream", h->deviceNum);
+    }
+    free(h->streams);
+    for (int e = 0; e < 2; ++e)
+    {
+        cudaEventDestroy(h->events[e]);
+        check("Destroying event", h->deviceNum);
+    }
+    free(h->events);
+    free(h->dataInput);
+    free(h->dataOutput);
+    free(h->boundaryTop);
+    free(h->boundaryBottom);
+    h->streams = nullptr;
+    h->events = nullptr;
+    h->dataInput = h->dataOutput = h->boundaryTop = h->boundaryBottom = nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------
+// band construction
+// ------------------------------------------------------------------------------------------------
+
+static Band base_band(const cuSten_t* h, const Plan* p, const double* coef)
+{
+    Band b{};
+    const Spec& s = p->spec;
+    b.nx = h->nx;
+    b.dir = s.dir;
+    b.L = s.dir == DIR_Y ? 0 : h->numStenLeft;
+    b.R = s.dir == DIR_Y ? 0 : h->numStenRight;
+    b.T = s.dir == DIR_X ? 0 : h->numStenTop;
+    b.B = s.dir == DIR_X ? 0 : h->numStenBottom;
+    b.H = s.dir == DIR_Y ? 1 : h->numStenHoriz;
+    b.V = s.dir == DIR_X ? 1 : h->numStenVert;
+    b.coef = coef;
+    b.ncoef = p->ncoef;
+    b.func = s.fun ? (const void*)h->devFunc : nullptr;
+    b.wrap_x = s.periodic && s.dir != DIR_Y;
+    b.xlo = 0;
+    b.xhi = h->nx;
+    if (!s.periodic && s.dir != DIR_Y)
+    {
+        b.xlo = b.L;
+        b.xhi = h->nx - b.R;
+        b.zero_right = (s.dir == DIR_X && !s.fun);  // 2d_x_np_kernel.cu:164-176
+    }
+    return b;
+}
+
+// rows [first_tile, last_tile] as one band
+static Band make_band(const cuSten_t* h, const Plan* p, const double* coef, int first_tile, int last_tile)
+{
+    Band b = base_band(h, p, coef);
+    const Spec& s = p->spec;
+    const int n = h->numTiles;
+    b.in = h->dataInput[first_tile];
+    b.out = h->dataOutput[first_tile];
+    b.rows = h->nyTile * (last_tile - first_tile + 1);
+    b.ylo = 0;
+    b.yhi = b.rows;
+    if (s.dir != DIR_X)
+    {
+        const bool at_top = first_tile == 0, at_bottom = last_tile == n - 1;
+        b.top = h->boundaryTop[first_tile];
+        b.bottom = h->boundaryBottom[last_tile];
+        bool phys_top = at_top, phys_bottom = at_bottom;  // band touches the physical edge of the global grid
+        if (p->slab_enabled)
+        {
+            if (at_top) b.top = p->slab_top;
+            if (at_bottom) b.bottom = p->slab_bottom;
+            phys_top = at_top && p->slab_first;
+            phys_bottom = at_bottom && p->slab_last;
+        }
+        b.have_top = s.periodic || !phys_top;
+        b.have_bottom = s.periodic || !phys_bottom;
+        if (!s.periodic)
+        {
+            if (phys_top) b.ylo = b.T;
+            if (phys_bottom) b.yhi = b.rows - b.B;
+        }
+        if (b.T == 0) b.have_top = 0;
+        if (b.B == 0) b.have_bottom = 0;
+    }
+    return b;
+}
+
+static bool tiles_contiguous(const cuSten_t* h)
+{
+    const ptrdiff_t off = (ptrdiff_t)h->nx * h->nyTile;
+    for (int t = 1; t < h->numTiles; ++t)
+    {
+        if (h->dataInput[t] != h->dataInput[0] + t * off) return false;
+        if (h->dataOutput[t] != h->dataOutput[0] + t * off) return false;
+        if (h->boundaryTop)
+        {
+            if (h->boundaryTop[t] != h->dataInput[t] - (ptrdiff_t)h->numStenTop * h->nx) return false;
+            if (h->boundaryBottom[t - 1] != h->dataInput[t]) return false;
+        }
+    }
+    return true;
+}
+
+static void rotate(cuSten_t* h)
+{
+    cudaStream_t s0 = h->streams[0];
+    h->streams[0] = h->streams[1];
+    h->streams[1] = h->streams[2];
+    h->streams[2] = s0;
+    std::swap(h->events[0], h->events[1]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Compute: three residency modes
+// ------------------------------------------------------------------------------------------------
+
+// device memory (or anything the GPU can address that needs no migration)
+static void compute_resident(cuSten_t* h, Plan* p, const double* coef)
+{
+    if (tiles_contiguous(h))
+    {
+        const Band b = make_band(h, p, coef, 0, h->numTiles - 1);
+        p->last_path = launch_band(b, h->streams[0]);
+        p->last_mode = 0;
+        check("Error computing grid", h->deviceNum);
+        return;
+    }
+    p->last_mode = 1;
+    for (int t = 0; t < h->numTiles; ++t)
+    {
+        const Band b = make_band(h, p, coef, t, t);
+        p->last_path = launch_band(b, h->streams[0]);
+        check("Error computing tile", h->deviceNum);
+        rotate(h);
+    }
+}
+
+static void prefetch(const void* ptr, size_t bytes, int dst, cudaStream_t st)
+{
+    if (ptr && bytes) cudaMemPrefetchAsync(ptr, bytes, dst, st);
+}
+
+static void prefetch_tile(cuSten_t* h, int t, int dst, cudaStream_t st)
+{
+    const size_t tile_bytes = (size_t)h->nx * h->nyTile * sizeof(double);
+    prefetch(h->dataInput[t], tile_bytes, dst, st);
+    prefetch(h->dataOutput[t], tile_bytes, dst, st);
+    if (h->boundaryTop)
+    {
+        prefetch(h->boundaryTop[t], (size_t)h->numBoundaryTop * sizeof(double), dst, st);
+        prefetch(h->boundaryBottom[t], (size_t)h->numBoundaryBottom * sizeof(double), dst, st);
+    }
+}
+
+// unified memory: the reference's load / compute / unload rotation, ordered on the device with
+// cudaStreamWaitEvent instead of host-side cudaEventSynchronize / cudaStreamSynchronize.
+static void compute_managed(cuSten_t* h, Plan* p, const double* coef, MemKind kcoef, bool offload)
+{
+    const int dev = h->deviceNum;
+    p->last_mode = 2;
+    if (kcoef == MK_MANAGED) prefetch(coef, (size_t)p->ncoef * sizeof(double), dev, h->streams[1]);
+    prefetch_tile(h, 0, dev, h->streams[1]);
+    cudaEventRecord(h->events[0], h->streams[1]);
+    for (int t = 0; t < h->numTiles; ++t)
+    {
+        cudaStreamWaitEvent(h->streams[0], h->events[0], 0);
+        const Band b = make_band(h, p, coef, t, t);
+        p->last_path = launch_band(b, h->streams[0]);
+        check("Error computing tile", dev);
+        if (offload)
+        {
+            const size_t tile_bytes = (size_t)h->nx * h->nyTile * sizeof(double);
+            prefetch(h->dataOutput[t], tile_bytes, cudaCpuDeviceId, h->streams[0]);
+            prefetch(h->dataInput[t], tile_bytes, cudaCpuDeviceId, h->streams[0]);
+        }
+        if (t + 1 < h->numTiles)
+        {
+            prefetch_tile(h, t + 1, dev, h->streams[1]);
+            cudaEventRecord(h->events[1], h->streams[1]);
+        }
+        rotate(h);
+    }
+    check("Error in managed tile pipeline", dev);
+}
+
+// host-resident grids (pinned or pageable): a ring of device slots; tile t+1 uploads on the load
+// stream while tile t computes and tile t-1 downloads.  Only the written rectangle is copied back,
+// so the untouched frame of the non-periodic variants keeps the caller's values.
+static void compute_staged(cuSten_t* h, Plan* p, const double* coef)
+{
+    const int dev = h->deviceNum;
+    const Spec& s = p->spec;
+    const int T = s.dir == DIR_X ? 0 : h->numStenTop;
+    const int B = s.dir == DIR_X ? 0 : h->numStenBottom;
+    const size_t nx = h->nx;
+    const size_t need_rows = (size_t)h->nyTile + T + B;
+    p->last_mode = 3;
+
+    if (p->stage_rows < need_rows)
+    {
+        for (int k = 0; k < 3; ++k) cudaStreamSynchronize(h->streams[k]);
+        const int ready = p->events_ready;
+        double* keep_coef = p->d_coef;
+        p->d_coef = nullptr;
+        p->events_ready = 0;
+        release_staging(p);
+        p->d_coef = keep_coef;
+        p->events_ready = ready;
+        const int slots = h->numTiles < kSlots ? h->numTiles : kSlots;
+        for (int k = 0; k < slots; ++k)
+        {
+            cudaMalloc(&p->d_in[k], need_rows * nx * sizeof(double));
+            cudaMalloc(&p->d_out[k], (size_t)h->nyTile * nx * sizeof(double));
+            check("Allocating staging slot", dev);
+        }
+        p->stage_rows = need_rows;
+    }
+    if (!p->events_ready)
+    {
+        for (int k = 0; k < kSlots; ++k)
+        {
+            cudaEventCreateWithFlags(&p->ev_loaded[k], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&p->ev_done[k], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&p->ev_unloaded[k], cudaEventDisableTiming);
+        }
+        p->events_ready = 1;
+    }
+
+    cudaStream_t s_comp = h->streams[0], s_load = h->streams[1], s_unload = h->streams[2];
+    const int slots = h->numTiles < kSlots ? h->numTiles : kSlots;
+    const size_t row_bytes = nx * sizeof(double);
+    for (int t = 0; t < h->numTiles; ++t)
+    {
+        const int k = t % slots;
+        Band b = make_band(h, p, coef, t, t);
+        // slot k is free once its previous occupant has been downloaded
+        if (t >= slots) cudaStreamWaitEvent(s_load, p->ev_unloaded[k], 0);
+        double* din = p->d_in[k];
+        if (b.have_top) cudaMemcpyAsync(din, b.top, (size_t)T * row_bytes, cudaMemcpyDefault, s_load);
+        cudaMemcpyAsync(din + (size_t)T * nx, b.in, (size_t)h->nyTile * row_bytes, cudaMemcpyDefault, s_load);
+        if (b.have_bottom)
+            cudaMemcpyAsync(din + ((size_t)T + h->nyTile) * nx, b.bottom, (size_t)B * row_bytes, cudaMemcpyDefault,
+                            s_load);
+        cudaEventRecord(p->ev_loaded[k], s_load);
+
+        double* host_out = b.out;
+        b.top = din;
+        b.in = din + (size_t)T * nx;
+        b.bottom = din + ((size_t)T + h->nyTile) * nx;
+        b.out = p->d_out[k];
+        cudaStreamWaitEvent(s_comp, p->ev_loaded[k], 0);
+        p->last_path = launch_band(b, s_comp);
+        check("Error computing staged tile", dev);
+        cudaEventRecord(p->ev_done[k], s_comp);
+
+        cudaStreamWaitEvent(s_unload, p->ev_done[k], 0);
+        const int x0 = b.xlo, x1 = b.zero_right ? b.nx : b.xhi;
+        if (b.yhi > b.ylo && x1 > x0)
+        {
+            const size_t o = (size_t)b.ylo * nx + x0;
+            if (x0 == 0 && x1 == b.nx)
+                cudaMemcpyAsync(host_out + o, b.out + o, (size_t)(b.yhi - b.ylo) * row_bytes, cudaMemcpyDefault,
+                                s_unload);
+            else
+                cudaMemcpy2DAsync(host_out + o, row_bytes, b.out + o, row_bytes, (size_t)(x1 - x0) * sizeof(double),
+                                  (size_t)(b.yhi - b.ylo), cudaMemcpyDefault, s_unload);
+        }
+        cudaEventRecord(p->ev_unloaded[k], s_unload);
+    }
+    // later work on the compute stream (and the caller's device-wide sync) sees the downloads
+    cudaStreamWaitEvent(s_comp, p->ev_unloaded[(h->numTiles - 1) % slots], 0);
+    check("Error in staged tile pipeline", dev);
+}
+
+void plan_compute(cuSten_t* h, bool offload)
+{
+    cudaSetDevice(h->deviceNum);
+    check("Setting current device", h->deviceNum);
+    Plan* p = plan_of(h);
+    if (!p)
+    {
+        printf("\ncuSten: handle was not created by cuStenCreate2D*\nprogram terminated ...\n\n");
+        exit(EXIT_FAILURE);
+    }
+    const Spec& s = p->spec;
+    const double* coef = s.fun ? h->coe : h->weights;
+    const MemKind kin = classify(h->dataInput[0]);
+    const MemKind kout = classify(h->dataOutput[0]);
+    MemKind kcoef = classify(coef);
+
+    // coefficients living in plain host memory are snapshotted to the device, stream-ordered
+    if (kcoef == MK_HOST)
+    {
+        if (!p->d_coef)
+        {
+            cudaMalloc(&p->d_coef, 1024 * sizeof(double));
+            check("Allocating coefficient buffer", h->deviceNum);
+        }
+        const int n = p->ncoef < 1024 ? p->ncoef : 1024;
+        cudaMemcpyAsync(p->d_coef, coef, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->streams[0]);
+        // every stream that may launch a kernel must see the snapshot
+        cudaEventRecord(h->events[1], h->streams[0]);
+        cudaStreamWaitEvent(h->streams[1], h->events[1], 0);
+        cudaStreamWaitEvent(h->streams[2], h->events[1], 0);
+        coef = p->d_coef;
+        kcoef = MK_DEVICE;
+    }
+
+    if (kin == MK_HOST || kout == MK_HOST) compute_staged(h, p, coef);
+    else if (kin == MK_MANAGED || kout == MK_MANAGED) compute_managed(h, p, coef, kcoef, offload);
+    else compute_resident(h, p, coef);
+}
+
+}  // namespace custen

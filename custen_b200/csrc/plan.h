@@ -1,0 +1,61 @@
+// Host-side plan and tile scheduler of cuSten-B200.
+//
+// Re-creates, stream-ordered and without host blocking, the reference's per-call tile loop
+// (cuSten/src/kernels/2d_xy_p_kernel.cu:542-657, state machine in SURVEY.md appendix B) and its plan
+// builders (cuSten/src/struct/custenCreateDestroy2D*.cu).  One generic implementation serves the 12
+// variants; the thin per-variant entry points live in api_cpp.cu.
+#ifndef CUSTEN_B200_PLAN_H
+#define CUSTEN_B200_PLAN_H
+
+#include "../../include/cuSten.h"
+#include "engine.h"
+
+namespace custen {
+
+struct Spec
+{
+    int dir;        // Dir
+    int periodic;   // 1 periodic, 0 non-periodic
+    int fun;        // 1 function-pointer variant
+};
+
+enum MemKind : int { MK_DEVICE = 0, MK_MANAGED = 1, MK_HOST = 2 };
+
+constexpr int kSlots = 3;  // staging ring depth for host-resident grids
+
+// Private state hung behind the public `streams` array (slot 3 = magic, slot 4 = Plan*), so that
+// sizeof(cuSten_t) and every public field offset stay as in the reference.
+struct Plan
+{
+    Spec spec;
+    int ncoef;
+    int last_path;           // Path of the most recent launch
+    int last_mode;           // 0 resident single launch, 1 resident per tile, 2 managed pipeline, 3 staged
+    // slab extension (multi-GPU layer): rows above / below the grid come from these buffers
+    const double* slab_top;
+    const double* slab_bottom;
+    int slab_first, slab_last;   // this slab touches the physical top / bottom of the global grid
+    int slab_enabled;
+    // staging for host-resident grids
+    double* d_in[kSlots];
+    double* d_out[kSlots];
+    double* d_coef;
+    size_t stage_rows;           // rows each d_in slot can hold
+    cudaEvent_t ev_loaded[kSlots], ev_done[kSlots], ev_unloaded[kSlots];
+    int events_ready;
+};
+
+Plan* plan_of(cuSten_t* h);
+
+void plan_create(cuSten_t* h, Spec spec, int deviceNum, int numTiles, int nx, int ny, int BLOCK_X, int BLOCK_Y,
+                 double* dataOutput, double* dataInput, double* coef, int H, int L, int R, int V, int T, int B,
+                 int numCoe, double* func);
+void plan_swap(cuSten_t* h, double* dataInput);
+void plan_destroy(cuSten_t* h);
+void plan_compute(cuSten_t* h, bool offload);
+
+MemKind classify(const void* p);
+
+}  // namespace custen
+
+#endif

@@ -1,0 +1,123 @@
+/* cuSten-B200: plain-C boundary of libcusten_b200.so.
+ *
+ * One extern "C" entry point per function of the reference's API for the 2D X / Y / XY path, with the
+ * reference's parameter lists (plain pointers and ints, no C++ or torch types), so that an FFI (ctypes, cgo,
+ * JNI ...) binds exactly what a C++ caller of the reference links against:
+ *
+ *   custenCreate2D<V>   <->  cuStenCreate2D<V>    cuSten/src/struct/cuSten_struct_functions.h:67-836
+ *   custenSwap2D<V>     <->  cuStenSwap2D<V>      (same header)
+ *   custenDestroy2D<V>  <->  cuStenDestroy2D<V>   (same header)
+ *   custenCompute2D<V>  <->  cuStenCompute2D<V>   cuSten/src/kernels/stencil_kernels.h:52-189
+ *   custenCheckError    <->  checkError           cuSten/src/util/util.h:43
+ *   <V> in { Xp, Xnp, XpFun, XnpFun, Yp, Ynp, YpFun, YnpFun, XYp, XYnp, XYpFun, XYnpFun }
+ *
+ * The handle is the reference's cuSten_t (cuSten/src/struct/cuSten_struct_type.h:84-122): caller-allocated,
+ * custen_handle_size() bytes, public fields at the reference's offsets.  Error behaviour is the reference's:
+ * every function returns void and a CUDA error terminates the process with a message (util/error.cu:43-53).
+ * Compute is asynchronous; completion is observed with custen_device_synchronize() (the reference's callers
+ * use cudaDeviceSynchronize, examples/src/2d_xy_p.cu:164-167).
+ *
+ * Everything below the "additive" line has no reference counterpart.
+ */
+#ifndef CUSTEN_B200_CUSTEN_C_H
+#define CUSTEN_B200_CUSTEN_C_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cuSten_c_handle cuSten_c_handle; /* == cuSten_t, opaque to C callers */
+
+#define CUSTEN_C_COMMON(V)                                                   \
+    void custenSwap2D##V(cuSten_c_handle* pt_cuSten, double* dataInput);     \
+    void custenDestroy2D##V(cuSten_c_handle* pt_cuSten);                     \
+    void custenCompute2D##V(cuSten_c_handle* pt_cuSten, int offload);
+
+#define CUSTEN_C_PREFIX cuSten_c_handle *pt_cuSten, int deviceNum, int numTiles, int nx, int ny, int BLOCK_X, int BLOCK_Y, \
+                        double *dataOutput, double *dataInput
+
+void custenCreate2DXp(CUSTEN_C_PREFIX, double* weights, int numSten, int numStenLeft, int numStenRight);
+CUSTEN_C_COMMON(Xp)
+void custenCreate2DXnp(CUSTEN_C_PREFIX, double* weights, int numSten, int numStenLeft, int numStenRight);
+CUSTEN_C_COMMON(Xnp)
+void custenCreate2DXpFun(CUSTEN_C_PREFIX, double* coe, int numSten, int numStenLeft, int numStenRight, int numCoe, double* func);
+CUSTEN_C_COMMON(XpFun)
+void custenCreate2DXnpFun(CUSTEN_C_PREFIX, double* coe, int numSten, int numStenLeft, int numStenRight, int numCoe, double* func);
+CUSTEN_C_COMMON(XnpFun)
+
+void custenCreate2DYp(CUSTEN_C_PREFIX, double* weights, int numSten, int numStenTop, int numStenBottom);
+CUSTEN_C_COMMON(Yp)
+void custenCreate2DYnp(CUSTEN_C_PREFIX, double* weights, int numSten, int numStenTop, int numStenBottom);
+CUSTEN_C_COMMON(Ynp)
+void custenCreate2DYpFun(CUSTEN_C_PREFIX, double* coe, int numSten, int numStenTop, int numStenBottom, int numCoe, double* func);
+CUSTEN_C_COMMON(YpFun)
+void custenCreate2DYnpFun(CUSTEN_C_PREFIX, double* coe, int numSten, int numStenTop, int numStenBottom, double* func);
+CUSTEN_C_COMMON(YnpFun)
+
+void custenCreate2DXYp(CUSTEN_C_PREFIX, double* weights, int numStenHoriz, int numStenLeft, int numStenRight,
+                       int numStenVert, int numStenTop, int numStenBottom);
+CUSTEN_C_COMMON(XYp)
+void custenCreate2DXYnp(CUSTEN_C_PREFIX, double* weights, int numStenHoriz, int numStenLeft, int numStenRight,
+                        int numStenVert, int numStenTop, int numStenBottom);
+CUSTEN_C_COMMON(XYnp)
+void custenCreate2DXYpFun(CUSTEN_C_PREFIX, double* coe, int numStenHoriz, int numStenLeft, int numStenRight,
+                          int numStenVert, int numStenTop, int numStenBottom, double* func);
+CUSTEN_C_COMMON(XYpFun)
+void custenCreate2DXYnpFun(CUSTEN_C_PREFIX, double* coe, int numStenHoriz, int numStenLeft, int numStenRight,
+                           int numStenVert, int numStenTop, int numStenBottom, double* func);
+CUSTEN_C_COMMON(XYnpFun)
+
+void custenCheckError(const char* action);
+
+/* ------------------------------------------------ additive ------------------------------------------------ */
+
+size_t custen_handle_size(void);                 /* sizeof(cuSten_t) */
+void custen_device_synchronize(void);            /* cudaDeviceSynchronize + checkError */
+
+/* Device function pointers of the user-function fixtures linked into this library (see
+ * custen_b200/csrc/builtin_funs.cuh); the value is what cudaMemcpyFromSymbol would give a C++ caller
+ * (examples/src/2d_xy_p_fun.cu:177-178).  Returns NULL for an unknown name.
+ * Names: second_diff_x weighted9_x weighted9_y weighted3_y weighted_xy cubic_xy */
+double* custen_builtin_fun(const char* name);
+
+/* Which kernel family / residency mode served the last Compute on this handle (engine.h Path, plan.h). */
+int custen_last_path(cuSten_c_handle* pt_cuSten);
+int custen_last_mode(cuSten_c_handle* pt_cuSten);
+uint64_t custen_launch_count(void);              /* kernels launched by this library so far */
+void custen_set_tuning(int force_fallback, int force_tile, int chunk_rows, int ctas_per_sm);
+
+/* Multi-GPU y-slab layer: the handle's grid is one slab of a taller global grid.  `top` / `bottom` point at the
+ * numStenTop rows above / numStenBottom rows below the slab (a local halo buffer filled by an exchange, or a
+ * neighbour GPU's memory mapped through custen_ipc_open); is_first / is_last say whether the slab touches the
+ * physical top / bottom edge of the global grid (matters for the non-periodic masks). */
+void custen_set_slab(cuSten_c_handle* pt_cuSten, const double* top, const double* bottom, int is_first, int is_last);
+
+/* CUDA IPC plumbing for the slab layer (one process per GPU): 64-byte handles travel over torch.distributed. */
+/* custen_ipc_export writes the handle of the allocation `dev_ptr` lives in and the byte offset of `dev_ptr`
+ * inside that allocation; the importer adds the offset to what custen_ipc_open returns. */
+void custen_ipc_export(const void* dev_ptr, void* handle64, size_t* offset_out);
+void* custen_ipc_open(const void* handle64);
+void custen_ipc_close(void* mapped_ptr);
+
+/* Event timing on the stream a handle launches on (streams[idx] of the handle). */
+void* custen_event_create(void);
+void custen_event_record(void* ev, cuSten_c_handle* pt_cuSten, int stream_idx);
+void custen_event_synchronize(void* ev);
+float custen_event_elapsed_ms(void* start, void* stop);
+void custen_event_destroy(void* ev);
+
+/* Pinned host buffers for the out-of-core path; unified-memory buffers (what the reference's callers use,
+ * examples/src/2d_x_p.cu:73-75). */
+void* custen_host_alloc(size_t bytes);
+void custen_host_free(void* p);
+void* custen_managed_alloc(size_t bytes);
+void custen_managed_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

@@ -1,0 +1,134 @@
+"""ctypes access to the oracle libraries under oracle/_ref/ — test infrastructure only.
+
+  libcusten_oracle.so  CPU restatement of the reference's stencil semantics (oracle/custen_oracle.c)
+  libserialcahn.so     the reference's serial CPU twin, compiled from /root/reference (CPU pin of the oracle)
+  libcusten_ref.so     the reference's CUDA library rebuilt for sm_100 + oracle/ref_shim.cu (GPU pin)
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+
+DIRS = {"X": 0, "Y": 1, "XY": 2}
+FUNS = {None: 0, "second_diff_x": 1, "weighted9_x": 2, "weighted9_y": 3, "weighted3_y": 4, "weighted_xy": 5,
+        "cubic_xy": 6}
+VARIANT_IDS = {v: i for i, v in enumerate(
+    ("Xp", "Xnp", "XpFun", "XnpFun", "Yp", "Ynp", "YpFun", "YnpFun", "XYp", "XYnp", "XYpFun", "XYnpFun"))}
+
+_dp = ctypes.POINTER(ctypes.c_double)
+
+
+def _ensure_built(name):
+    path = os.path.join(REFDIR, name)
+    if not os.path.exists(path):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=False, capture_output=True)
+    return path if os.path.exists(path) else None
+
+
+def variant_parts(variant):
+    d = "XY" if variant.startswith("XY") else variant[0]
+    rest = variant[len(d):]
+    return d, rest.startswith("p"), rest.endswith("Fun")
+
+
+_oracle = None
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        path = _ensure_built("libcusten_oracle.so")
+        if path is None:
+            raise RuntimeError("oracle/_ref/libcusten_oracle.so missing and could not be built (make -C oracle)")
+        lib = ctypes.CDLL(path)
+        lib.custen_oracle_sweep.argtypes = [ctypes.c_int] * 3 + [_dp, _dp, ctypes.c_int, ctypes.c_int, _dp] + [ctypes.c_int] * 6
+        lib.custen_oracle_sweep.restype = ctypes.c_int
+        _oracle = lib
+    return _oracle
+
+
+def oracle_sweep(variant, inp, out, coef, H=1, L=0, R=0, V=1, T=0, B=0, fun=None, periodic_bits=None):
+    """CPU oracle for one sweep.  `out` is modified in place (pre-fill it) and returned."""
+    d, periodic, is_fun = variant_parts(variant)
+    assert is_fun == (fun is not None)
+    inp = np.ascontiguousarray(inp, dtype=np.float64)
+    coef = np.ascontiguousarray(coef, dtype=np.float64)
+    assert out.dtype == np.float64 and out.flags.c_contiguous
+    ny, nx = inp.shape
+    bits = (3 if periodic else 0) if periodic_bits is None else periodic_bits
+    rc = oracle().custen_oracle_sweep(DIRS[d], bits, FUNS[fun], inp.ctypes.data_as(_dp), out.ctypes.data_as(_dp), nx, ny,
+                                      coef.ctypes.data_as(_dp), H, L, R, V, T, B)
+    assert rc == 0
+    return out
+
+
+_serial = None
+
+
+def serial():
+    """The reference's serial CPU twin as a library, or None when it is not available (no /root/reference)."""
+    global _serial
+    if _serial is None:
+        path = _ensure_built("libserialcahn.so")
+        if path is None:
+            return None
+        lib = ctypes.CDLL(path)
+        for name in ("linearRHS", "nonlinearRHS"):
+            f = getattr(lib, name)
+            f.argtypes = [_dp, _dp, _dp] + [ctypes.c_int] * 5
+            f.restype = None
+        _serial = lib
+    return _serial
+
+
+_ref = None
+
+
+def ref_gpu():
+    """The reference's CUDA kernels rebuilt for sm_100 (needs a GPU to call)."""
+    global _ref
+    if _ref is None:
+        path = _ensure_built("libcusten_ref.so")
+        if path is None:
+            return None
+        lib = ctypes.CDLL(path)
+        lib.ref_sweep.argtypes = ([ctypes.c_int, _dp, _dp] + [ctypes.c_int] * 5 + [_dp] + [ctypes.c_int] * 7
+                                  + [ctypes.c_char_p, ctypes.c_int])
+        lib.ref_sweep.restype = ctypes.c_int
+        lib.ref_time.argtypes = ([ctypes.c_int] * 6 + [_dp] + [ctypes.c_int] * 7 + [ctypes.c_char_p, ctypes.c_int,
+                                                                                   ctypes.c_int])
+        lib.ref_time.restype = ctypes.c_double
+        _ref = lib
+    return _ref
+
+
+def ref_sweep(variant, inp, out, coef, H=1, L=0, R=0, V=1, T=0, B=0, fun=None, tiles=1, block=(32, 32), offload=0):
+    """Run the reference's own CUDA kernels.  Returns `out` (modified in place) or None if the reference has no
+    working implementation of the variant (XpFun)."""
+    lib = ref_gpu()
+    inp = np.ascontiguousarray(inp, dtype=np.float64)
+    coef = np.ascontiguousarray(coef, dtype=np.float64)
+    ny, nx = inp.shape
+    rc = lib.ref_sweep(VARIANT_IDS[variant], inp.ctypes.data_as(_dp), out.ctypes.data_as(_dp), nx, ny, tiles, block[0],
+                       block[1], coef.ctypes.data_as(_dp), coef.size, H, L, R, V, T, B,
+                       fun.encode() if fun else None, offload)
+    return out if rc == 0 else None
+
+
+def ref_time(variant, nx, ny, coef, H=1, L=0, R=0, V=1, T=0, B=0, fun=None, tiles=1, block=(32, 32), warmup=3, iters=10):
+    lib = ref_gpu()
+    coef = np.ascontiguousarray(coef, dtype=np.float64)
+    return lib.ref_time(VARIANT_IDS[variant], nx, ny, tiles, block[0], block[1], coef.ctypes.data_as(_dp), coef.size,
+                        H, L, R, V, T, B, fun.encode() if fun else None, warmup, iters)
+
+
+def bits_equal(a, b):
+    return np.array_equal(np.ascontiguousarray(a).view(np.int64), np.ascontiguousarray(b).view(np.int64))
+
+
+def count_diff(a, b):
+    return int(np.count_nonzero(np.ascontiguousarray(a).view(np.int64) != np.ascontiguousarray(b).view(np.int64)))

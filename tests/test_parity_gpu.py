@@ -1,0 +1,233 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the C ABI of libcusten_b200.so.
+
+Bar: bit-exact against (a) the CPU oracle and (b) the reference's own CUDA kernels rebuilt for sm_100, on the
+same seeded inputs, untouched regions of `out` included (pre-filled with a sentinel).
+"""
+import numpy as np
+import pytest
+
+import cases
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+import custen_b200 as cs  # noqa: E402
+import gpu_util as gu  # noqa: E402
+
+ACC_SHAPES = {(3, 1), (5, 1), (7, 1), (9, 1), (1, 3), (1, 5), (1, 7), (1, 9), (3, 3), (5, 5)}
+
+
+def _oracle(c, inp):
+    return ol.oracle_sweep(c["variant"], inp, np.full_like(inp, cases.SENTINEL), c["coef"], **cases.case_kwargs(c))
+
+
+def _expected_path(c):
+    if c["fun"]:
+        return "stream_tile"
+    d = ol.variant_parts(c["variant"])[0]
+    H = 1 if d == "Y" else c["H"]
+    V = 1 if d == "X" else c["V"]
+    return "stream_acc" if (H, V) in ACC_SHAPES else "stream_tile"
+
+
+@pytest.fixture(autouse=True)
+def _reset_tuning():
+    cs.set_tuning(0, 0, 0, 0)
+    yield
+    cs.set_tuning(0, 0, 0, 0)
+
+
+@pytest.mark.parametrize("c", cases.CASES, ids=cases.CASE_IDS)
+def test_new_engine_vs_oracle_and_reference_kernels(c):
+    inp = cases.case_input(c)
+    want = _oracle(c, inp)
+    got, path, mode = gu.run_ours(c, inp, return_path=True)
+    assert path == _expected_path(c), path
+    assert mode == "resident"
+    assert ol.count_diff(got, want) == 0, "new engine differs from the CPU oracle"
+    ref = ol.ref_sweep(c["variant"], inp, np.full_like(inp, cases.SENTINEL), c["coef"], tiles=c["tiles"],
+                       block=c["block"], **cases.case_kwargs(c))
+    if ref is None:
+        assert c["variant"] == "XpFun"  # no working reference: oracle only
+        return
+    assert ol.count_diff(ref, want) == 0, "CPU oracle differs from the reference's CUDA kernels"
+    assert ol.count_diff(got, ref) == 0
+
+
+@pytest.mark.parametrize("c", cases.CASES, ids=cases.CASE_IDS)
+def test_fallback_family(c):
+    """The plain-load kernel family is an independent implementation: it must agree bit for bit too."""
+    cs.set_tuning(1, 0, 0, 0)
+    inp = cases.case_input(c)
+    got, path, _ = gu.run_ours(c, inp, return_path=True)
+    assert path == "fallback"
+    assert ol.count_diff(got, _oracle(c, inp)) == 0
+
+
+@pytest.mark.parametrize("c", [c for c in cases.CASES if not c["fun"]], ids=[c["name"] for c in cases.CASES if not c["fun"]])
+def test_tile_family_serves_weights(c):
+    cs.set_tuning(0, 1, 0, 0)
+    inp = cases.case_input(c)
+    got, path, _ = gu.run_ours(c, inp, return_path=True)
+    assert path == "stream_tile"
+    assert ol.count_diff(got, _oracle(c, inp)) == 0
+
+
+@pytest.mark.parametrize("chunk,cps", [(16, 1), (24, 2), (40, 3), (1000000, 1)])
+@pytest.mark.parametrize("name", ["x_p_9pt_random", "y_p_9pt_tiles", "xy_p_biharmonic", "xy_np_5x5", "xy_p_fun_cubic",
+                                  "y_np_fun_example", "xy_p_3x5_tile_family"])
+def test_work_decomposition_seams(name, chunk, cps):
+    """Chunk seams, stage remainders and CTA counts must not show in the result."""
+    c = next(x for x in cases.CASES if x["name"] == name)
+    cs.set_tuning(0, 0, chunk, cps)
+    inp = cases.case_input(c)
+    assert ol.count_diff(gu.run_ours(c, inp), _oracle(c, inp)) == 0
+
+
+KIND_CASES = ["x_p_9pt_random", "x_np_5pt_tiles", "x_np_fun_example", "y_p_9pt_tiles", "y_np_9pt_example",
+              "y_p_fun_example", "xy_p_cross_tiles", "xy_np_cross_example", "xy_np_5x5", "xy_p_fun_cubic",
+              "xy_np_fun_cubic_tiles"]
+
+
+@pytest.mark.parametrize("kind,mode", [("managed", "managed_pipeline"), ("pinned", "staged"), ("pageable", "staged")])
+@pytest.mark.parametrize("name", KIND_CASES)
+@pytest.mark.parametrize("offload", [cs.DEVICE, cs.HOST])
+def test_memory_kinds_and_offload(name, kind, mode, offload):
+    """Unified memory (what the reference requires), pinned and pageable host grids through the tile scheduler."""
+    c = next(x for x in cases.CASES if x["name"] == name)
+    inp = cases.case_input(c)
+    got, path, m = gu.run_ours(c, inp, kind=kind, offload=offload, return_path=True)
+    assert m == mode
+    assert ol.count_diff(got, _oracle(c, inp)) == 0
+
+
+@pytest.mark.parametrize("tiles", [1, 2, 4, 8])
+@pytest.mark.parametrize("name", ["xy_p_biharmonic", "xy_np_5x5", "y_np_9pt_example", "xy_p_fun_cubic"])
+def test_num_tiles_do_not_change_results(name, tiles):
+    c = next(x for x in cases.CASES if x["name"] == name)
+    inp = cases.case_input(c)
+    want = _oracle(c, inp)
+    for kind in ("device", "pinned"):
+        assert ol.count_diff(gu.run_ours(c, inp, kind=kind, tiles=tiles), want) == 0
+
+
+@pytest.mark.parametrize("name", ["x_p_5pt", "y_p_5pt", "xy_p_cross_tiles", "xy_p_fun_cubic", "xy_np_5x5"])
+def test_swap_time_stepping(name):
+    """Create -> (Compute, Swap) x 3, as a time stepper uses the API (Swap re-aliases in/out and the seams)."""
+    c = next(x for x in cases.CASES if x["name"] == name)
+    scale = 1.0 / max(1.0, float(np.sum(np.abs(c["coef"]))))
+    coef = c["coef"] * scale  # keep the iteration bounded
+    inp = cases.case_input(c)
+    a, b = inp.copy(), np.full_like(inp, cases.SENTINEL)
+    for _ in range(3):
+        ol.oracle_sweep(c["variant"], a, b, coef, **cases.case_kwargs(c))
+        a, b = b, a
+    want_in, want_out = a, b  # after 3 swaps: `a` holds the newest field
+
+    buf = gu.Buffers("device", inp, np.full_like(inp, cases.SENTINEL), coef)
+    st = cs.Stencil2D(c["variant"], c["nx"], c["ny"], buf.out, buf.inp, buf.coef, H=c["H"], L=c["L"], R=c["R"], V=c["V"],
+                      T=c["T"], B=c["B"], fun=c["fun"], numCoe=c["numCoe"], numTiles=c["tiles"], block=c["block"])
+    cur_in, cur_out = buf.inp, buf.out
+    for _ in range(3):
+        st.compute(cs.DEVICE)
+        cs.device_synchronize()
+        st.swap(cur_out)  # the array that becomes the next input
+        cur_in, cur_out = cur_out, cur_in
+    # three swaps: the newest field sits in the array that started as `out`
+    newest = buf.result("out")
+    older = buf.result("in")
+    st.destroy()
+    buf.free()
+    assert ol.count_diff(newest, want_in) == 0
+    assert ol.count_diff(older, want_out) == 0
+
+
+def test_shapes_the_tma_path_cannot_take_use_the_fallback():
+    rng = np.random.default_rng(5)
+    # odd nx: rows are not 16-byte aligned
+    c = cases._c("odd_nx", "XYp", 255, 64, 1, (5, 8), rng.uniform(-1, 1, 9), H=3, L=1, R=1, V=3, T=1, B=1)
+    inp = cases.case_input(c)
+    got, path, _ = gu.run_ours(c, inp, return_path=True)
+    assert path == "fallback" and ol.count_diff(got, _oracle(c, inp)) == 0
+    # very wide window
+    c = cases._c("wide", "Xp", 256, 32, 1, (32, 8), rng.uniform(-1, 1, 21), H=21, L=10, R=10)
+    inp = cases.case_input(c)
+    got, path, _ = gu.run_ours(c, inp, return_path=True)
+    assert path == "fallback" and ol.count_diff(got, _oracle(c, inp)) == 0
+    # grids the reference itself cannot handle (one block wide / ragged sizes) still work here
+    c = cases._c("ragged", "XYnp", 100, 37, 1, (32, 32), rng.uniform(-1, 1, 9), H=3, L=1, R=1, V=3, T=1, B=1)
+    inp = cases.case_input(c)
+    assert ol.count_diff(gu.run_ours(c, inp), _oracle(c, inp)) == 0
+    c = cases._c("ragged_p", "XYp", 300, 41, 1, (32, 32), rng.uniform(-1, 1, 25), H=5, L=2, R=2, V=5, T=2, B=2)
+    inp = cases.case_input(c)
+    assert ol.count_diff(gu.run_ours(c, inp), _oracle(c, inp)) == 0
+
+
+def test_public_handle_fields_follow_the_reference_formulas():
+    """cuSten_t fields a caller may read (custenCreateDestroy2DXYp.cu:83-240)."""
+    c = next(x for x in cases.CASES if x["name"] == "xy_p_cross_tiles")
+    inp = cases.case_input(c)
+    buf = gu.Buffers("device", inp, np.zeros_like(inp), c["coef"])
+    st = cs.Stencil2D("XYp", c["nx"], c["ny"], buf.out, buf.inp, buf.coef, H=3, L=1, R=1, V=3, T=1, B=1, numTiles=4,
+                      block=(32, 16))
+    h = st.handle
+    assert (h.deviceNum, h.numStreams, h.numTiles, h.nx, h.ny, h.nyTile) == (0, 3, 4, 512, 512, 128)
+    assert (h.numSten, h.numStenHoriz, h.numStenVert) == (9, 3, 3)
+    assert (h.nxLocal, h.nyLocal) == (32 + 2, 16 + 2)
+    assert h.mem_shared == (34 * 18 + 9) * 8
+    assert (h.xGrid, h.yGrid) == (16, 8)
+    assert (h.numBoundaryTop, h.numBoundaryBottom) == (512, 512)
+    assert h.weights == buf.coef
+    st.destroy()
+    buf.free()
+
+
+@pytest.mark.parametrize("variant,n", [("Xp", 8192), ("XYp", 16384), ("XYnp", 16384), ("XYpFun", 16384)])
+def test_full_size_properties(variant, n):
+    """BASELINE.json sizes: the two independent kernel families agree bit for bit, and periodic sweeps commute
+    with a cyclic shift of the grid (checked on the device)."""
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    inp = torch.rand((n, n), generator=g, device="cuda", dtype=torch.float64) * 2 - 1
+    if variant == "Xp":
+        coef, kw = cases.weights_d2_8th(2 * np.pi / n), dict(H=9, L=4, R=4)
+    elif variant == "XYpFun":
+        coef, kw = cases.weights_laplace5(0.25), dict(H=3, L=1, R=1, V=3, T=1, B=1, fun="cubic_xy")
+    else:
+        coef, kw = cases.weights_cross_xy(2 * np.pi / n, 2 * np.pi / n), dict(H=3, L=1, R=1, V=3, T=1, B=1)
+    tcoef = torch.from_numpy(coef).cuda()
+    tiles = 4 if variant == "XYnp" else 1
+
+    def sweep(x, fallback):
+        out = torch.full_like(x, cases.SENTINEL)
+        cs.set_tuning(1 if fallback else 0, 0, 0, 0)
+        st = cs.Stencil2D(variant, n, n, out, x, tcoef, numTiles=tiles, **kw)
+        st.compute(cs.DEVICE)
+        cs.device_synchronize()
+        st.destroy()
+        return out
+
+    a = sweep(inp, False)
+    b = sweep(inp, True)
+    assert torch.equal(a.view(torch.int64), b.view(torch.int64))
+    del b
+    if variant != "XYnp":
+        sh = torch.roll(inp, shifts=(129, -77), dims=(0, 1)).contiguous()
+        c2 = sweep(sh, False)
+        assert torch.equal(torch.roll(a, shifts=(129, -77), dims=(0, 1)).view(torch.int64), c2.view(torch.int64))
+    else:
+        assert bool((a[0] == cases.SENTINEL).all()) and bool((a[:, -1] == cases.SENTINEL).all())
+
+
+def test_reference_kernels_at_config2_size():
+    """Config 2 (2d_x_p, 8192^2): new engine vs the reference's kernel at the full BASELINE size."""
+    n = 8192
+    inp = cases.field("sinx", n, n)
+    coef = cases.weights_d2_8th(2 * np.pi / n)
+    c = cases._c("cfg2", "Xp", n, n, 2, (32, 32), coef, H=9, L=4, R=4)
+    ref = ol.ref_sweep("Xp", inp, np.zeros_like(inp), coef, tiles=2, block=(32, 32), H=9, L=4, R=4)
+    got = gu.run_ours(c, inp, out_init=np.zeros_like(inp))
+    assert ol.count_diff(got, ref) == 0
