@@ -80,9 +80,9 @@ def build_cases():
     cs.append(_c("x_p_4pt_asym", "Xp", 256, 64, 1, (32, 16), rng.uniform(-1, 1, 4), H=4, L=1, R=2))
     cs.append(_c("x_np_9pt_example", "Xnp", 1024, 512, 1, (32, 16), weights_d2_8th(dx(1024)), H=9, L=4, R=4, fld="sinx"))
     cs.append(_c("x_np_5pt_tiles", "Xnp", 512, 256, 4, (32, 16), weights_d2_4th(dx(512)), H=5, L=2, R=2))
-    cs.append(_c("x_np_fun_example", "XnpFun", 1024, 512, 4, (32, 32), [1.0 / dx(1024) ** 2], H=3, L=1, R=1,
+    cs.append(_c("x_np_fun_example", "XnpFun", 1024, 512, 4, (32, 16), [1.0 / dx(1024) ** 2], H=3, L=1, R=1,
                  fun="second_diff_x", numCoe=1, fld="sinx"))
-    cs.append(_c("x_np_fun_9pt", "XnpFun", 512, 128, 1, (32, 32), weights_d2_8th(dx(512)), H=9, L=4, R=4,
+    cs.append(_c("x_np_fun_9pt", "XnpFun", 512, 128, 1, (32, 16), weights_d2_8th(dx(512)), H=9, L=4, R=4,
                  fun="weighted9_x", numCoe=9))
     cs.append(_c("x_p_fun_3pt", "XpFun", 512, 128, 2, (32, 32), [1.0 / dx(512) ** 2], H=3, L=1, R=1,
                  fun="second_diff_x", numCoe=1))
