@@ -212,6 +212,11 @@ def variant_table(cs, torch, n, steps, warmup, peak):
         gpts = n * n / ms / 1e6
         table[v] = {"gpoints_per_s": round(gpts, 2), "hbm_gbs": round(gpts * ALG_BYTES_PER_POINT, 1),
                     "frac_of_peak": round(gpts * ALG_BYTES_PER_POINT / peak, 4), "path": st.path}
+        if v.endswith("Fun"):  # the same call through the opaque device pointer (unregistered user function)
+            cs.set_tuning(force_opaque=1)
+            ms = time_resident(cs, st, steps, warmup) / steps
+            cs.set_tuning()
+            table[v]["opaque_pointer_gpoints_per_s"] = round(n * n / ms / 1e6, 2)
         st.destroy()
     return table
 

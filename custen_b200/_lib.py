@@ -68,7 +68,7 @@ def load():
     lib.custen_last_path.argtypes, lib.custen_last_path.restype = [_c_void_p], _c_int
     lib.custen_last_mode.argtypes, lib.custen_last_mode.restype = [_c_void_p], _c_int
     lib.custen_launch_count.argtypes, lib.custen_launch_count.restype = [], ctypes.c_uint64
-    lib.custen_set_tuning.argtypes, lib.custen_set_tuning.restype = [_c_int] * 4, None
+    lib.custen_set_tuning.argtypes, lib.custen_set_tuning.restype = [_c_int] * 5, None
     lib.custen_set_slab.argtypes, lib.custen_set_slab.restype = [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int], None
     lib.custen_ipc_export.argtypes, lib.custen_ipc_export.restype = [_c_void_p, _c_void_p, _c_void_p], None
     lib.custen_ipc_open.argtypes, lib.custen_ipc_open.restype = [_c_void_p], ctypes.c_void_p

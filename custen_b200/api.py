@@ -15,7 +15,7 @@ from . import _lib
 DEVICE = 0  # cuSten/cuSten.h:30
 HOST = 1    # cuSten/cuSten.h:31
 
-PATH_NAMES = {0: "none", 1: "stream_acc", 2: "stream_tile", 3: "fallback"}
+PATH_NAMES = {0: "none", 1: "stream_acc", 2: "stream_tile", 3: "fallback", 4: "stream_inline"}
 MODE_NAMES = {0: "resident", 1: "resident_per_tile", 2: "managed_pipeline", 3: "staged"}
 
 
@@ -114,8 +114,8 @@ def launch_count():
     return int(_lib.load().custen_launch_count())
 
 
-def set_tuning(force_fallback=0, force_tile=0, chunk_rows=0, ctas_per_sm=0):
-    _lib.load().custen_set_tuning(force_fallback, force_tile, chunk_rows, ctas_per_sm)
+def set_tuning(force_fallback=0, force_tile=0, chunk_rows=0, ctas_per_sm=0, force_opaque=0):
+    _lib.load().custen_set_tuning(force_fallback, force_tile, chunk_rows, ctas_per_sm, force_opaque)
 
 
 def set_slab(handle, top, bottom, is_first, is_last):

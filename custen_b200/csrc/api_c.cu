@@ -1,5 +1,6 @@
 // extern "C" boundary of libcusten_b200.so (declared in include/custen_c.h).
 #include "../../include/custen_c.h"
+#include "../../include/cuSten_fun.h"
 #include "builtin_funs.cuh"
 #include "plan.h"
 
@@ -16,6 +17,15 @@ __device__ cuStenFunY fp_weighted9_y = custen_funs::weighted9_y;
 __device__ cuStenFunY fp_weighted3_y = custen_funs::weighted3_y;
 __device__ cuStenFunXY fp_weighted_xy = custen_funs::weighted_xy;
 __device__ cuStenFunXY fp_cubic_xy = custen_funs::cubic_xy;
+
+// ... and registered, so that the library's own fixtures take the inlined road (custen_set_tuning can force the
+// opaque-pointer road for comparison).
+CUSTEN_REGISTER_FUN_X_AS(custen_funs::second_diff_x, second_diff_x)
+CUSTEN_REGISTER_FUN_X_AS(custen_funs::weighted9_x, weighted9_x)
+CUSTEN_REGISTER_FUN_Y_AS(custen_funs::weighted9_y, weighted9_y)
+CUSTEN_REGISTER_FUN_Y_AS(custen_funs::weighted3_y, weighted3_y)
+CUSTEN_REGISTER_FUN_XY_AS(custen_funs::weighted_xy, weighted_xy)
+CUSTEN_REGISTER_FUN_XY_AS(custen_funs::cubic_xy, cubic_xy)
 
 extern "C" {
 
@@ -104,13 +114,14 @@ int custen_last_mode(cuSten_c_handle* h)
 }
 uint64_t custen_launch_count(void) { return launches_total(); }
 
-void custen_set_tuning(int force_fallback, int force_tile, int chunk_rows, int ctas_per_sm)
+void custen_set_tuning(int force_fallback, int force_tile, int chunk_rows, int ctas_per_sm, int force_opaque)
 {
     Tuning& t = tuning();
     t.force_fallback = force_fallback;
     t.force_tile = force_tile;
     t.chunk_rows = chunk_rows;
     t.ctas_per_sm = ctas_per_sm;
+    t.force_opaque = force_opaque;
 }
 
 void custen_set_slab(cuSten_c_handle* h, const double* top, const double* bottom, int is_first, int is_last)

@@ -44,7 +44,8 @@ enum Path : int
     PATH_NONE = 0,
     PATH_STREAM_ACC = 1,   // TMA-fed row streaming, register accumulators (weights variants)
     PATH_STREAM_TILE = 2,  // TMA-fed row streaming, shared window handed to the user function
-    PATH_FALLBACK = 3      // plain-load halo tile (odd nx, unaligned rows, exotic shapes)
+    PATH_FALLBACK = 3,     // plain-load halo tile (odd nx, unaligned rows, exotic shapes)
+    PATH_STREAM_INLINE = 4 // as PATH_STREAM_TILE, user function registered and inlined (include/cuSten_fun.h)
 };
 
 struct Tuning
@@ -53,6 +54,7 @@ struct Tuning
     int chunk_rows;        // 0 = choose automatically
     int ctas_per_sm;       // 0 = choose automatically
     int force_tile;        // 1: weights variants use PATH_STREAM_TILE (tests)
+    int force_opaque;      // 1: Fun variants always call through the device pointer, registered or not
 };
 
 Tuning& tuning();

@@ -1,0 +1,537 @@
+// cuSten-B200 streaming kernels (sm_100a), header form.
+//
+// Lives in a header because the Fun variants have two roads to the user's function:
+//   * through the opaque device pointer the reference API carries (one indirect call per point), and
+//   * inlined, when the translation unit that defines the function registers it with CUSTEN_REGISTER_FUN_*
+//     (include/cuSten_fun.h): the kernel template below is then instantiated around the function itself and
+//     Compute picks that instance when cuSten_t::devFunc equals the registered pointer.
+//
+// Design (all variants):
+//   persistent CTAs, one producer warp + NT consumer threads.  The producer walks the CTA's work items
+//   (column strip x row chunk) and feeds a ring of NS shared-memory stages with 1-D TMA bulk copies
+//   (cp.async.bulk, completion on an mbarrier), ONE GRID ROW PER COPY.  Because the source of every row is
+//   just an address, periodic wrap in x (up to three pieces per row), wrap / tile seams / remote halo rows
+//   in y (band.top / band.bottom) are index arithmetic, never extra copies or special-cased blocks.
+//   Every input element leaves HBM once; outputs are written once.
+#ifndef CUSTEN_B200_STREAM_KERNELS_CUH
+#define CUSTEN_B200_STREAM_KERNELS_CUH
+
+#include "engine.h"
+
+namespace custen {
+
+typedef double (*FunX)(double*, double*, int);
+typedef double (*FunY)(double*, double*, int, int);
+typedef double (*FunXY)(double*, double*, int, int, int, int);
+
+__device__ __forceinline__ const double* band_row(const Band& b, int r)
+{
+    // r is band-local: [-T, 0) -> top strip, [0, rows) -> the band, [rows, rows+B) -> bottom strip
+    if (r < 0) return b.top + (ptrdiff_t)(r + b.T) * b.nx;
+    if (r >= b.rows) return b.bottom + (ptrdiff_t)(r - b.rows) * b.nx;
+    return b.in + (ptrdiff_t)r * b.nx;
+}
+
+__device__ __forceinline__ bool band_row_exists(const Band& b, int r)
+{
+    if (r < 0) return b.have_top && r >= -b.T;
+    if (r >= b.rows) return b.have_bottom && r < b.rows + b.B;
+    return true;
+}
+
+// ---- PTX helpers -------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {}
+}
+// 1-D TMA: global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void consumer_bar(int nthreads)
+{
+    asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
+
+// ---- geometry shared by host and device ----------------------------------------------------------------------
+
+struct StreamArgs
+{
+    Band b;
+    int TW;             // strip width in columns
+    int Lp, Rp;         // halo widths rounded up to even (keeps every copy 16-byte aligned)
+    int PW;             // shared-memory row pitch in doubles = Lp + TW + Rp
+    int Beff;           // V - 1 - T: rows below the centre that the window reaches
+    int PFX;            // rows kept in front of each stage (tile family: V - 1, acc family: 0)
+    int nstrips, nchunks, chunk_rows, nitems;
+    int stage_doubles;  // (PFX + SR) * PW
+};
+
+struct StageDesc
+{
+    int x0;      // first column of the strip
+    int row0;    // band-local input row held by stage row 0
+    int nrows;   // valid rows in this stage; < 0 terminates the consumers
+    int out_lo;  // output rows this work item may write: [out_lo, out_hi)
+    int out_hi;
+    int pad[3];
+};
+
+constexpr int SMEM_BAR_OFF = 0;       // full[NS], empty[NS]
+constexpr int SMEM_DESC_OFF = 128;    // NS descriptors of 32 B
+constexpr int SMEM_COEF_OFF = 512;    // up to 128 coefficients
+constexpr int SMEM_STAGE_OFF = 1536;  // stage ring
+constexpr int MAX_SMEM_COEF = 128;
+
+// Producer: one warp.  Lane l owns stage row l: it works out where that grid row lives (band, top strip,
+// bottom strip; wrapped columns) and issues up to three bulk copies for it.
+template <int SR, int NS>
+__device__ __forceinline__ void producer_loop(const StreamArgs& a, unsigned char* smem, int lane)
+{
+    static_assert(SR <= 32, "one producer lane per stage row");
+    const Band& b = a.b;
+    const uint32_t full0 = smem_u32(smem + SMEM_BAR_OFF);
+    const uint32_t empty0 = full0 + 8 * NS;
+    StageDesc* desc = reinterpret_cast<StageDesc*>(smem + SMEM_DESC_OFF);
+    const uint32_t stage0 = smem_u32(smem + SMEM_STAGE_OFF);
+    const uint32_t stage_bytes = (uint32_t)a.stage_doubles * 8u;
+    const uint32_t pitch_bytes = (uint32_t)a.PW * 8u;
+
+    int s = 0;
+    uint32_t ph = 0;
+    for (int item = blockIdx.x; item < a.nitems; item += gridDim.x)
+    {
+        const int strip = item % a.nstrips;
+        const int chunk = item / a.nstrips;
+        const int x0 = strip * a.TW;
+        const int out_lo = chunk * a.chunk_rows;
+        const int out_hi = min(out_lo + a.chunk_rows, b.rows);
+        const int in_lo = out_lo - b.T;
+        const int in_hi = out_hi + a.Beff;
+
+        // unwrapped column range this strip needs: [u0, u1)
+        const int xe = min(x0 + a.TW, b.nx);
+        const int u0 = x0 - a.Lp, u1 = xe + a.Rp;
+        // pieces: [u0,0) wrapped from the right edge, [max(u0,0), min(u1,nx)), [nx,u1) wrapped from the left edge
+        const int m0 = max(u0, 0), m1 = min(u1, b.nx);
+        const int lw = (b.wrap_x && u0 < 0) ? -u0 : 0;
+        const int rw = (b.wrap_x && u1 > b.nx) ? u1 - b.nx : 0;
+        const uint32_t row_bytes = (uint32_t)(m1 - m0 + lw + rw) * 8u;
+
+        for (int r0 = in_lo; r0 < in_hi; r0 += SR)
+        {
+            const int nrows = min(SR, in_hi - r0);
+            mbar_wait(empty0 + 8 * s, ph ^ 1);
+
+            const int r = r0 + lane;
+            const bool live = lane < nrows && band_row_exists(b, r);
+            const uint32_t total = __reduce_add_sync(0xffffffffu, live ? row_bytes : 0u);
+
+            const uint32_t bar = full0 + 8 * s;
+            if (lane == 0)
+            {
+                StageDesc d;
+                d.x0 = x0;
+                d.row0 = r0;
+                d.nrows = nrows;
+                d.out_lo = out_lo;
+                d.out_hi = out_hi;
+                desc[s] = d;
+                if (total) mbar_arrive_expect_tx(bar, total);
+                else mbar_arrive(bar);
+            }
+            __syncwarp();
+            if (live)
+            {
+                const double* src = band_row(b, r);
+                const uint32_t dst = stage0 + s * stage_bytes + (uint32_t)(a.PFX + lane) * pitch_bytes;
+                bulk_g2s(dst + (uint32_t)(m0 - u0) * 8u, src + m0, (uint32_t)(m1 - m0) * 8u, bar);
+                if (lw) bulk_g2s(dst, src + (b.nx - lw), (uint32_t)lw * 8u, bar);
+                if (rw) bulk_g2s(dst + (uint32_t)(b.nx - u0) * 8u, src, (uint32_t)rw * 8u, bar);
+            }
+            if (++s == NS) { s = 0; ph ^= 1; }
+        }
+    }
+    // terminate the consumers
+    mbar_wait(empty0 + 8 * s, ph ^ 1);
+    if (lane == 0)
+    {
+        StageDesc d;
+        d.x0 = 0; d.row0 = 0; d.nrows = -1; d.out_lo = 0; d.out_hi = 0;
+        desc[s] = d;
+        mbar_arrive(full0 + 8 * s);
+    }
+}
+
+template <int NS>
+__device__ __forceinline__ void stream_prologue(unsigned char* smem, int consumer_arrivals)
+{
+    if (threadIdx.x == 0)
+    {
+        const uint32_t full0 = smem_u32(smem + SMEM_BAR_OFF);
+        for (int i = 0; i < NS; ++i)
+        {
+            mbar_init(full0 + 8 * i, 1);
+            mbar_init(full0 + 8 * (NS + i), consumer_arrivals);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+}
+
+// Store one finished pair of outputs honouring the non-periodic column masks.
+struct ColMask
+{
+    bool s0, s1;  // store the computed value
+    bool z0, z1;  // store 0.0 instead (Xnp right strip)
+};
+__device__ __forceinline__ ColMask make_colmask(const Band& b, int gx)
+{
+    ColMask m;
+    const bool in0 = gx < b.nx, in1 = gx + 1 < b.nx;
+    m.s0 = in0 && gx >= b.xlo && gx < b.xhi;
+    m.s1 = in1 && gx + 1 >= b.xlo && gx + 1 < b.xhi;
+    m.z0 = in0 && b.zero_right && gx >= b.xhi;
+    m.z1 = in1 && b.zero_right && gx + 1 >= b.xhi;
+    return m;
+}
+__device__ __forceinline__ void store_pair(double* p, double vx, double vy, const ColMask& m)
+{
+    if (m.s0 && m.s1) { *reinterpret_cast<double2*>(p) = make_double2(vx, vy); return; }
+    if (m.s0) p[0] = vx; else if (m.z0) p[0] = 0.0;
+    if (m.s1) p[1] = vy; else if (m.z1) p[1] = 0.0;
+}
+
+// ---- stream_acc_kernel: weights variants, compile-time H x V, weights in registers ----------------------------
+// A consumer thread owns two adjacent columns (TW = 2 NT) and sweeps down the rows.  For each arriving row it
+// reads its H+1 wide window with 128-bit shared loads and feeds V partial sums, one per output row still in
+// flight; the sum whose last tap row just arrived is stored with a 128-bit store and its slot restarts at 0.0.
+// Each output's chain is therefore fma(w, v, sum) from sum = 0.0, rows top to bottom, taps left to right:
+// the reference's order (2d_xy_p_kernel.cu:507-520), hence bit-identical results.
+
+template <int NT, int SR, int NS, int H, int V, int LODD, int MINB>
+__global__ void __launch_bounds__(NT + 32, MINB) stream_acc_kernel(const __grid_constant__ StreamArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    stream_prologue<NS>(smem, NT / 32);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == NT / 32)
+    {
+        producer_loop<SR, NS>(a, smem, lane);
+        return;
+    }
+
+    const Band& b = a.b;
+    const int t = threadIdx.x;
+    const uint32_t full0 = smem_u32(smem + SMEM_BAR_OFF);
+    const uint32_t empty0 = full0 + 8 * NS;
+    const StageDesc* desc = reinterpret_cast<const StageDesc*>(smem + SMEM_DESC_OFF);
+    const double* stage0 = reinterpret_cast<const double*>(smem + SMEM_STAGE_OFF);
+
+    double w[H * V];
+#pragma unroll
+    for (int k = 0; k < H * V; ++k) w[k] = __ldg(b.coef + k);
+
+    double ax[V], ay[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) ax[j] = ay[j] = 0.0;
+
+    constexpr int NQ = (LODD + H + 2) / 2;  // 16-byte loads covering columns [2t, 2t + LODD + H]
+
+    int s = 0;
+    uint32_t ph = 0;
+    for (;;)
+    {
+        mbar_wait(full0 + 8 * s, ph);
+        const StageDesc d = desc[s];
+        if (d.nrows < 0) break;
+        const double* buf = stage0 + (size_t)s * a.stage_doubles;
+        const int gx = d.x0 + 2 * t;
+        const ColMask cm = make_colmask(b, gx);
+        double* obase = b.out + (ptrdiff_t)(d.row0 - a.Beff) * b.nx + gx;
+
+#pragma unroll
+        for (int i = 0; i < SR; ++i)
+        {
+            if (i < d.nrows)
+            {
+                const double2* rp = reinterpret_cast<const double2*>(buf + i * a.PW) + t;
+                double win[2 * NQ];
+#pragma unroll
+                for (int q = 0; q < NQ; ++q)
+                {
+                    const double2 v = rp[q];
+                    win[2 * q] = v.x;
+                    win[2 * q + 1] = v.y;
+                }
+#pragma unroll
+                for (int j = 0; j < V; ++j)
+                {
+#pragma unroll
+                    for (int ii = 0; ii < H; ++ii)
+                    {
+                        ax[j] = fma(w[j * H + ii], win[LODD + ii], ax[j]);
+                        ay[j] = fma(w[j * H + ii], win[LODD + ii + 1], ay[j]);
+                    }
+                }
+                const int yo = d.row0 + i - a.Beff;
+                if (yo >= d.out_lo && yo < d.out_hi && yo >= b.ylo && yo < b.yhi)
+                    store_pair(obase + (ptrdiff_t)i * b.nx, ax[V - 1], ay[V - 1], cm);
+#pragma unroll
+                for (int j = V - 1; j > 0; --j)
+                {
+                    ax[j] = ax[j - 1];
+                    ay[j] = ay[j - 1];
+                }
+                ax[0] = 0.0;
+                ay[0] = 0.0;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + 8 * s);
+        if (++s == NS) { s = 0; ph ^= 1; }
+    }
+}
+
+// ---- stream_tile_kernel: a contiguous window in shared memory, handed to an operator --------------------------
+// One column per consumer thread (TW = NT): a warp reads consecutive 8-byte words, conflict free.  Each stage
+// buffer has PFX = V-1 rows in front of the rows the producer fills; after a stage is consumed its last V-1
+// rows are copied there for the next stage, so every window is contiguous with pitch PW and the user function
+// sees exactly the tile layout the reference gives it (data, loc, jump).
+
+struct OpWeights  // run-time H x V weights (shapes without a register-accumulator instance)
+{
+    static __device__ __forceinline__ double apply(const Band& b, double* buf, double* cf, int tl, int PW)
+    {
+        double sum = 0.0;
+        for (int j = 0; j < b.V; ++j)
+            for (int i = 0; i < b.H; ++i) sum = fma(cf[j * b.H + i], buf[tl + j * PW + i], sum);
+        return sum;
+    }
+};
+struct OpPtrX  // opaque device pointer, X contract: loc = centre
+{
+    static __device__ __forceinline__ double apply(const Band& b, double* buf, double* cf, int tl, int PW)
+    {
+        return ((FunX)b.func)(buf, cf, tl + b.L);
+    }
+};
+struct OpPtrY  // loc = centre, jump = pitch
+{
+    static __device__ __forceinline__ double apply(const Band& b, double* buf, double* cf, int tl, int PW)
+    {
+        return ((FunY)b.func)(buf, cf, tl + b.T * PW, PW);
+    }
+};
+struct OpPtrXY  // loc = TOP-LEFT of the window (2d_xy_p_fun_kernel.cu:521)
+{
+    static __device__ __forceinline__ double apply(const Band& b, double* buf, double* cf, int tl, int PW)
+    {
+        return ((FunXY)b.func)(buf, cf, tl, PW, b.H, b.V);
+    }
+};
+// Registered functions: the call is direct, so the compiler inlines the user's code into the sweep.
+// LC / TC / HC / VC > 0 pin the stencil extents at compile time (loops in the user function then unroll).
+template <FunX F, int LC>
+struct OpInlineX
+{
+    static __device__ __forceinline__ double apply(const Band& b, double* buf, double* cf, int tl, int PW)
+    {
+        return F(buf, cf, tl + (LC >= 0 ? LC : b.L));
+    }
+};
+template <FunY F, int TC>
+struct OpInlineY
+{
+    static __device__ __forceinline__ double apply(const Band& b, double* buf, double* cf, int tl, int PW)
+    {
+        return F(buf, cf, tl + (TC >= 0 ? TC : b.T) * PW, PW);
+    }
+};
+template <FunXY F, int HC, int VC>
+struct OpInlineXY
+{
+    static __device__ __forceinline__ double apply(const Band& b, double* buf, double* cf, int tl, int PW)
+    {
+        return F(buf, cf, tl, PW, HC > 0 ? HC : b.H, VC > 0 ? VC : b.V);
+    }
+};
+
+template <int NT, int SR, int NS, int MINB, class Op>
+__global__ void __launch_bounds__(NT + 32, MINB) stream_tile_kernel(const __grid_constant__ StreamArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    stream_prologue<NS>(smem, 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == NT / 32)
+    {
+        producer_loop<SR, NS>(a, smem, lane);
+        return;
+    }
+
+    const Band& b = a.b;
+    const int t = threadIdx.x;
+    const uint32_t full0 = smem_u32(smem + SMEM_BAR_OFF);
+    const uint32_t empty0 = full0 + 8 * NS;
+    const StageDesc* desc = reinterpret_cast<const StageDesc*>(smem + SMEM_DESC_OFF);
+    double* stage0 = reinterpret_cast<double*>(smem + SMEM_STAGE_OFF);
+    double* cf = reinterpret_cast<double*>(smem + SMEM_COEF_OFF);
+
+    for (int k = t; k < b.ncoef; k += NT) cf[k] = b.coef[k];
+    consumer_bar(NT);
+
+    const int PW = a.PW, PFX = a.PFX;
+    const int dlt = a.Lp - b.L;  // the window of strip column c starts at pitch column c + dlt
+
+    int s = 0;
+    uint32_t ph = 0;
+    for (;;)
+    {
+        mbar_wait(full0 + 8 * s, ph);
+        const StageDesc d = desc[s];
+        if (d.nrows < 0) break;
+        double* buf = stage0 + (size_t)s * a.stage_doubles;
+
+        const int gx = d.x0 + t;
+        const bool st = gx < b.nx && gx >= b.xlo && gx < b.xhi;
+        const bool zr = gx < b.nx && b.zero_right && gx >= b.xhi;
+        // rows of this stage that produce an output this item owns
+        const int ybase = d.row0 - a.Beff;
+        const int i_lo = max(0, max(d.out_lo, b.ylo) - ybase);
+        const int i_hi = min(d.nrows, min(d.out_hi, b.yhi) - ybase);
+        if (st)
+        {
+            double* o = b.out + (ptrdiff_t)ybase * b.nx + gx;
+            const int tl0 = t + dlt;  // top-left of the window of stage row 0 (buffer row i <-> input row yo - T)
+            if (i_lo == 0 && i_hi == SR)
+            {
+#pragma unroll
+                for (int i = 0; i < SR; ++i) o[(ptrdiff_t)i * b.nx] = Op::apply(b, buf, cf, tl0 + i * PW, PW);
+            }
+            else
+            {
+                for (int i = i_lo; i < i_hi; ++i) o[(ptrdiff_t)i * b.nx] = Op::apply(b, buf, cf, tl0 + i * PW, PW);
+            }
+        }
+        else if (zr)
+        {
+            double* o = b.out + (ptrdiff_t)ybase * b.nx + gx;
+            for (int i = i_lo; i < i_hi; ++i) o[(ptrdiff_t)i * b.nx] = 0.0;
+        }
+
+        // carry the last V-1 rows over to the front of the next stage
+        if (PFX > 0)
+        {
+            const int sn = (s + 1 == NS) ? 0 : s + 1;
+            double* nxt = stage0 + (size_t)sn * a.stage_doubles;
+            const double* src = buf + d.nrows * PW;
+            for (int e = t; e < PFX * PW; e += NT) nxt[e] = src[e];
+        }
+        consumer_bar(NT);
+        if (t == 0) mbar_arrive(empty0 + 8 * s);
+        if (++s == NS) { s = 0; ph ^= 1; }
+    }
+}
+
+// ---- launch plumbing shared by the library and by registering translation units ------------------------------
+
+constexpr int TILE_NT = 256;  // tile family: consumer threads = strip width
+constexpr int TILE_SR = 8;
+constexpr int TILE_NS = 3;
+
+struct LaunchGeom
+{
+    int grid;
+    int threads;
+    size_t smem;
+};
+
+// Defined in kernels.cu: raises the kernel's dynamic shared-memory limit, asks the occupancy calculator how many
+// CTAs of `kernel` fit on an SM (an opaque user function may need any number of registers), splits the band
+// into work items accordingly and fills the item fields of `a`.
+LaunchGeom plan_stream_launch(StreamArgs& a, const void* kernel, int threads, size_t smem);
+
+template <int MINB, class Op>
+inline void launch_tile_instance(StreamArgs& a, cudaStream_t st)
+{
+    auto kernel = stream_tile_kernel<TILE_NT, TILE_SR, TILE_NS, MINB, Op>;
+    const size_t smem = SMEM_STAGE_OFF + (size_t)TILE_NS * a.stage_doubles * sizeof(double);
+    const LaunchGeom g = plan_stream_launch(a, (const void*)kernel, TILE_NT + 32, smem);
+    kernel<<<g.grid, g.threads, g.smem, st>>>(a);
+}
+
+// Signature of a registered (inlined) launcher: picks the instance for the band's extents and launches it.
+typedef void (*InlineLauncher)(StreamArgs& a, cudaStream_t st);
+
+constexpr int INLINE_MINB = 3;  // inlined instances are compiled for three CTAs per SM
+
+template <FunX F>
+inline void launch_inline_x(StreamArgs& a, cudaStream_t st)
+{
+    if (a.b.L == 1) launch_tile_instance<INLINE_MINB, OpInlineX<F, 1>>(a, st);
+    else if (a.b.L == 4) launch_tile_instance<INLINE_MINB, OpInlineX<F, 4>>(a, st);
+    else launch_tile_instance<INLINE_MINB, OpInlineX<F, -1>>(a, st);
+}
+template <FunY F>
+inline void launch_inline_y(StreamArgs& a, cudaStream_t st)
+{
+    if (a.b.T == 1) launch_tile_instance<INLINE_MINB, OpInlineY<F, 1>>(a, st);
+    else if (a.b.T == 4) launch_tile_instance<INLINE_MINB, OpInlineY<F, 4>>(a, st);
+    else launch_tile_instance<INLINE_MINB, OpInlineY<F, -1>>(a, st);
+}
+template <FunXY F>
+inline void launch_inline_xy(StreamArgs& a, cudaStream_t st)
+{
+    if (a.b.H == 3 && a.b.V == 3) launch_tile_instance<INLINE_MINB, OpInlineXY<F, 3, 3>>(a, st);
+    else if (a.b.H == 5 && a.b.V == 5) launch_tile_instance<INLINE_MINB, OpInlineXY<F, 5, 5>>(a, st);
+    else launch_tile_instance<INLINE_MINB, OpInlineXY<F, 0, 0>>(a, st);
+}
+
+// Registry of inlined instances, keyed by the device address of the user function.
+struct FunRegistration
+{
+    int dir;                               // Dir
+    const void* (*resolve)();              // reads the device pointer (cudaMemcpyFromSymbol), called lazily
+    InlineLauncher launch;
+    const void* dev_ptr;                   // filled on first use
+    FunRegistration* next;
+};
+void register_fun(FunRegistration* r);     // defined in kernels.cu
+
+}  // namespace custen
+
+#endif

@@ -87,7 +87,7 @@ double* custen_builtin_fun(const char* name);
 int custen_last_path(cuSten_c_handle* pt_cuSten);
 int custen_last_mode(cuSten_c_handle* pt_cuSten);
 uint64_t custen_launch_count(void);              /* kernels launched by this library so far */
-void custen_set_tuning(int force_fallback, int force_tile, int chunk_rows, int ctas_per_sm);
+void custen_set_tuning(int force_fallback, int force_tile, int chunk_rows, int ctas_per_sm, int force_opaque);
 
 /* Multi-GPU y-slab layer: the handle's grid is one slab of a taller global grid.  `top` / `bottom` point at the
  * numStenTop rows above / numStenBottom rows below the slab (a local halo buffer filled by an exchange, or a

@@ -27,7 +27,7 @@ def _oracle(c, inp):
 
 def _expected_path(c):
     if c["fun"]:
-        return "stream_tile"
+        return "stream_inline"  # the library's fixtures are registered (include/cuSten_fun.h)
     d = ol.variant_parts(c["variant"])[0]
     H = 1 if d == "Y" else c["H"]
     V = 1 if d == "X" else c["V"]
@@ -71,6 +71,16 @@ def test_fallback_family(c):
     inp = cases.case_input(c)
     got, path, _ = gu.run_ours(c, inp, return_path=True)
     assert path == "fallback"
+    assert ol.count_diff(got, _oracle(c, inp)) == 0
+
+
+@pytest.mark.parametrize("c", [c for c in cases.CASES if c["fun"]], ids=[c["name"] for c in cases.CASES if c["fun"]])
+def test_opaque_function_pointer_road(c):
+    """Fun variants through the indirect call, as an unregistered user function would run."""
+    cs.set_tuning(force_opaque=1)
+    inp = cases.case_input(c)
+    got, path, _ = gu.run_ours(c, inp, return_path=True)
+    assert path == "stream_tile"
     assert ol.count_diff(got, _oracle(c, inp)) == 0
 
 
