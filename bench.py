@@ -40,6 +40,7 @@ WORKLOADS = {
     "x_p_8192": ("Xp", 8192, 1, "configs[1]: 2D X periodic 9-pt 8th-order d2/dx2 (2d_x_p example), 8192^2 FP64"),
     "xy_np_16384_t4": ("XYnp", 16384, 4, "configs[2]: 2D XY non-periodic 3x3 cross stencil, 16384^2 FP64, numTiles=4"),
     "xy_p_fun_16384": ("XYpFun", 16384, 1, "2D XY periodic Fun stencil (c^3-c, 3x3), 16384^2 FP64"),
+    "xy_p_16384": ("XYp", 16384, 1, "2D XY periodic 3x3 cross stencil (2d_xy_p example), 16384^2 FP64"),
 }
 
 

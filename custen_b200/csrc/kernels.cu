@@ -141,14 +141,20 @@ static int launch_fallback(const Band& b, cudaStream_t st)
 }
 
 // ---- streaming launch geometry -----------------------------------------------------------------------------
-
-constexpr int ACC_NT = 128;  // consumer threads per CTA -> 256-column strips (two columns per thread)
-constexpr int ACC_SR = 8;    // rows per stage
-constexpr int ACC_NS = 4;    // stages in the ring
+// Register-accumulator family: geometry per window shape, from a sweep on B200 (tools/tune_stream.cu):
+// consumer threads, columns per thread, rows per stage, ring depth, CTAs per SM.  A stage height that is a
+// multiple of V lets the accumulator slots rotate by renaming instead of by register moves.
+template <int H, int V> struct AccGeom { static constexpr int NT = 512, CPT = 1, SR = 8, NS = 3, MAXCPS = 1; };
+template <int H> struct AccGeom<H, 1> { static constexpr int NT = 256, CPT = 2, SR = 8, NS = 3, MAXCPS = 1; };
+template <> struct AccGeom<1, 3> { static constexpr int NT = 256, CPT = 1, SR = 6, NS = 3, MAXCPS = 2; };
+template <> struct AccGeom<1, 5> { static constexpr int NT = 512, CPT = 1, SR = 10, NS = 3, MAXCPS = 1; };
+template <> struct AccGeom<1, 7> { static constexpr int NT = 512, CPT = 1, SR = 7, NS = 3, MAXCPS = 1; };
+template <> struct AccGeom<1, 9> { static constexpr int NT = 512, CPT = 1, SR = 9, NS = 3, MAXCPS = 1; };
+template <> struct AccGeom<5, 5> { static constexpr int NT = 512, CPT = 1, SR = 8, NS = 3, MAXCPS = 1; };
 
 // Work decomposition: column strips x row chunks, chunk height chosen so that the item count is (just under)
 // a whole number of waves of resident CTAs.
-LaunchGeom plan_stream_launch(StreamArgs& a, const void* kernel, int threads, size_t smem)
+LaunchGeom plan_stream_launch(StreamArgs& a, const void* kernel, int threads, size_t smem, int max_cps)
 {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int cps = tuning().ctas_per_sm;
@@ -156,6 +162,7 @@ LaunchGeom plan_stream_launch(StreamArgs& a, const void* kernel, int threads, si
     {
         cps = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, kernel, threads, smem);
+        if (max_cps > 0 && cps > max_cps) cps = max_cps;
         if (cps < 1) cps = 1;
     }
     const int ncta = sm_count() * cps;
@@ -184,11 +191,18 @@ LaunchGeom plan_stream_launch(StreamArgs& a, const void* kernel, int threads, si
     return g;
 }
 
-template <typename K>
-static void launch_acc(K kernel, StreamArgs& a, cudaStream_t st)
+template <int H, int V, int LODD>
+static void launch_acc(StreamArgs& a, cudaStream_t st)
 {
-    const size_t smem = SMEM_STAGE_OFF + (size_t)ACC_NS * a.stage_doubles * sizeof(double);
-    const LaunchGeom g = plan_stream_launch(a, (const void*)kernel, ACC_NT + 32, smem);
+    typedef AccGeom<H, V> G;
+    a.TW = G::CPT * G::NT;
+    a.PW = a.Lp + a.TW + a.Rp;
+    a.nstrips = (a.b.nx + a.TW - 1) / a.TW;
+    a.PFX = 0;
+    a.stage_doubles = G::SR * a.PW;
+    auto kernel = stream_acc_kernel<G::NT, G::SR, G::NS, H, V, LODD, G::CPT, 1>;
+    const size_t smem = SMEM_STAGE_OFF + (size_t)G::NS * a.stage_doubles * sizeof(double);
+    const LaunchGeom g = plan_stream_launch(a, (const void*)kernel, G::NT + 32, smem, G::MAXCPS);
     kernel<<<g.grid, g.threads, g.smem, st>>>(a);
 }
 
@@ -241,17 +255,12 @@ int launch_band(const Band& b, cudaStream_t st)
     const bool lodd = (b.L & 1) != 0;
     if (!b.func && !tu.force_tile)
     {
-        a.TW = 2 * ACC_NT;
-        a.PW = a.Lp + a.TW + a.Rp;
-        a.nstrips = (b.nx + a.TW - 1) / a.TW;
-        a.PFX = 0;
-        a.stage_doubles = ACC_SR * a.PW;
-#define ACC_CASE(HH, VV)                                                                          \
-    if (b.H == HH && b.V == VV)                                                                   \
-    {                                                                                             \
-        if (lodd) launch_acc(stream_acc_kernel<ACC_NT, ACC_SR, ACC_NS, HH, VV, 1, 1>, a, st);     \
-        else launch_acc(stream_acc_kernel<ACC_NT, ACC_SR, ACC_NS, HH, VV, 0, 1>, a, st);          \
-        return PATH_STREAM_ACC;                                                                   \
+#define ACC_CASE(HH, VV)                                   \
+    if (b.H == HH && b.V == VV)                            \
+    {                                                      \
+        if (lodd) launch_acc<HH, VV, 1>(a, st);            \
+        else launch_acc<HH, VV, 0>(a, st);                 \
+        return PATH_STREAM_ACC;                            \
     }
         ACC_CASE(3, 1) ACC_CASE(5, 1) ACC_CASE(7, 1) ACC_CASE(9, 1)
         ACC_CASE(1, 3) ACC_CASE(1, 5) ACC_CASE(1, 7) ACC_CASE(1, 9)
@@ -259,14 +268,9 @@ int launch_band(const Band& b, cudaStream_t st)
 #undef ACC_CASE
     }
 
-    a.TW = TILE_NT;
-    a.PW = a.Lp + a.TW + a.Rp;
-    a.nstrips = (b.nx + a.TW - 1) / a.TW;
-    a.PFX = b.V - 1;
-    a.stage_doubles = (a.PFX + TILE_SR) * a.PW;
     if (!b.func)
     {
-        launch_tile_instance<3, OpWeights>(a, st);
+        launch_tile_instance<false, 2, OpWeights>(a, st);
         return PATH_STREAM_TILE;
     }
     if (!tu.force_opaque)
@@ -278,9 +282,9 @@ int launch_band(const Band& b, cudaStream_t st)
         }
     }
     // opaque pointer: no minimum-blocks bound, the callee's register need is unknown until device link
-    if (b.dir == DIR_X) launch_tile_instance<1, OpPtrX>(a, st);
-    else if (b.dir == DIR_Y) launch_tile_instance<1, OpPtrY>(a, st);
-    else launch_tile_instance<1, OpPtrXY>(a, st);
+    if (b.dir == DIR_X) launch_tile_instance<false, 1, OpPtrX>(a, st);
+    else if (b.dir == DIR_Y) launch_tile_instance<false, 1, OpPtrY>(a, st);
+    else launch_tile_instance<false, 1, OpPtrXY>(a, st);
     return PATH_STREAM_TILE;
 }
 

@@ -106,7 +106,8 @@ struct StageDesc
     int nrows;   // valid rows in this stage; < 0 terminates the consumers
     int out_lo;  // output rows this work item may write: [out_lo, out_hi)
     int out_hi;
-    int pad[3];
+    int first;   // 1: first stage of a work item (register accumulators restart)
+    int pad[2];
 };
 
 constexpr int SMEM_BAR_OFF = 0;       // full[NS], empty[NS]
@@ -168,6 +169,7 @@ __device__ __forceinline__ void producer_loop(const StreamArgs& a, unsigned char
                 d.nrows = nrows;
                 d.out_lo = out_lo;
                 d.out_hi = out_hi;
+                d.first = (r0 == in_lo);
                 desc[s] = d;
                 if (total) mbar_arrive_expect_tx(bar, total);
                 else mbar_arrive(bar);
@@ -189,7 +191,7 @@ __device__ __forceinline__ void producer_loop(const StreamArgs& a, unsigned char
     if (lane == 0)
     {
         StageDesc d;
-        d.x0 = 0; d.row0 = 0; d.nrows = -1; d.out_lo = 0; d.out_hi = 0;
+        d.x0 = 0; d.row0 = 0; d.nrows = -1; d.out_lo = 0; d.out_hi = 0; d.first = 0;
         desc[s] = d;
         mbar_arrive(full0 + 8 * s);
     }
@@ -235,15 +237,16 @@ __device__ __forceinline__ void store_pair(double* p, double vx, double vy, cons
 }
 
 // ---- stream_acc_kernel: weights variants, compile-time H x V, weights in registers ----------------------------
-// A consumer thread owns two adjacent columns (TW = 2 NT) and sweeps down the rows.  For each arriving row it
-// reads its H+1 wide window with 128-bit shared loads and feeds V partial sums, one per output row still in
+// A consumer thread owns CPT adjacent columns (TW = CPT * NT) and sweeps down the rows.  For each arriving row it
+// reads its window from shared memory (128-bit loads when CPT == 2) and feeds V partial sums, one per output row still in
 // flight; the sum whose last tap row just arrived is stored with a 128-bit store and its slot restarts at 0.0.
 // Each output's chain is therefore fma(w, v, sum) from sum = 0.0, rows top to bottom, taps left to right:
 // the reference's order (2d_xy_p_kernel.cu:507-520), hence bit-identical results.
 
-template <int NT, int SR, int NS, int H, int V, int LODD, int MINB>
+template <int NT, int SR, int NS, int H, int V, int LODD, int CPT, int MINB>
 __global__ void __launch_bounds__(NT + 32, MINB) stream_acc_kernel(const __grid_constant__ StreamArgs a)
 {
+    static_assert(CPT == 1 || CPT == 2, "columns per thread");
     extern __shared__ __align__(128) unsigned char smem[];
     stream_prologue<NS>(smem, NT / 32);
 
@@ -265,11 +268,17 @@ __global__ void __launch_bounds__(NT + 32, MINB) stream_acc_kernel(const __grid_
 #pragma unroll
     for (int k = 0; k < H * V; ++k) w[k] = __ldg(b.coef + k);
 
-    double ax[V], ay[V];
+    double acc[V][CPT];
 #pragma unroll
-    for (int j = 0; j < V; ++j) ax[j] = ay[j] = 0.0;
+    for (int j = 0; j < V; ++j)
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) acc[j][c] = 0.0;
 
-    constexpr int NQ = (LODD + H + 2) / 2;  // 16-byte loads covering columns [2t, 2t + LODD + H]
+    // CPT == 2: 16-byte loads covering pitch columns [2t, 2t + LODD + H]; CPT == 1: H 8-byte loads from t + LODD
+    constexpr int NQ = (LODD + H + 2) / 2;
+    constexpr int NW = CPT == 2 ? 2 * NQ : H;
+    constexpr int W0 = CPT == 2 ? LODD : 0;
+    constexpr bool ROT = (SR % V == 0) && V > 1;
 
     int s = 0;
     uint32_t ph = 0;
@@ -279,45 +288,78 @@ __global__ void __launch_bounds__(NT + 32, MINB) stream_acc_kernel(const __grid_
         const StageDesc d = desc[s];
         if (d.nrows < 0) break;
         const double* buf = stage0 + (size_t)s * a.stage_doubles;
-        const int gx = d.x0 + 2 * t;
+        const int gx = d.x0 + CPT * t;
         const ColMask cm = make_colmask(b, gx);
         double* obase = b.out + (ptrdiff_t)(d.row0 - a.Beff) * b.nx + gx;
+        if (ROT && d.first)
+        {
+#pragma unroll
+            for (int j = 0; j < V; ++j)
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) acc[j][c] = 0.0;
+        }
 
 #pragma unroll
         for (int i = 0; i < SR; ++i)
         {
             if (i < d.nrows)
             {
-                const double2* rp = reinterpret_cast<const double2*>(buf + i * a.PW) + t;
-                double win[2 * NQ];
-#pragma unroll
-                for (int q = 0; q < NQ; ++q)
+                double win[NW];
+                if (CPT == 2)
                 {
-                    const double2 v = rp[q];
-                    win[2 * q] = v.x;
-                    win[2 * q + 1] = v.y;
+                    const double2* rp = reinterpret_cast<const double2*>(buf + i * a.PW) + t;
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q)
+                    {
+                        const double2 v = rp[q];
+                        win[2 * q] = v.x;
+                        win[2 * q + 1] = v.y;
+                    }
                 }
+                else
+                {
+                    const double* rp = buf + i * a.PW + t + LODD;
+#pragma unroll
+                    for (int q = 0; q < H; ++q) win[q] = rp[q];
+                }
+                // Tap row j of this input row belongs to the output whose chain is in slot (i - j) mod V when the
+                // stage height is a multiple of V (slots then line up from stage to stage and nothing moves);
+                // otherwise slot j, with a shift after every row.
 #pragma unroll
                 for (int j = 0; j < V; ++j)
                 {
+                    constexpr int VV = V;
+                    const int sl = ROT ? ((i - j) % VV + VV) % VV : j;
 #pragma unroll
                     for (int ii = 0; ii < H; ++ii)
                     {
-                        ax[j] = fma(w[j * H + ii], win[LODD + ii], ax[j]);
-                        ay[j] = fma(w[j * H + ii], win[LODD + ii + 1], ay[j]);
+#pragma unroll
+                        for (int c = 0; c < CPT; ++c) acc[sl][c] = fma(w[j * H + ii], win[W0 + ii + c], acc[sl][c]);
                     }
                 }
+                const int done = ROT ? ((i - (V - 1)) % V + V) % V : V - 1;  // slot whose last tap row just arrived
                 const int yo = d.row0 + i - a.Beff;
                 if (yo >= d.out_lo && yo < d.out_hi && yo >= b.ylo && yo < b.yhi)
-                    store_pair(obase + (ptrdiff_t)i * b.nx, ax[V - 1], ay[V - 1], cm);
-#pragma unroll
-                for (int j = V - 1; j > 0; --j)
                 {
-                    ax[j] = ax[j - 1];
-                    ay[j] = ay[j - 1];
+                    double* p = obase + (ptrdiff_t)i * b.nx;
+                    if (CPT == 2) store_pair(p, acc[done][0], acc[done][CPT - 1], cm);
+                    else if (cm.s0) *p = acc[done][0];
+                    else if (cm.z0) *p = 0.0;
                 }
-                ax[0] = 0.0;
-                ay[0] = 0.0;
+                if (ROT)
+                {
+#pragma unroll
+                    for (int c = 0; c < CPT; ++c) acc[done][c] = 0.0;
+                }
+                else
+                {
+#pragma unroll
+                    for (int j = V - 1; j > 0; --j)
+#pragma unroll
+                        for (int c = 0; c < CPT; ++c) acc[j][c] = acc[j - 1][c];
+#pragma unroll
+                    for (int c = 0; c < CPT; ++c) acc[0][c] = 0.0;
+                }
             }
         }
         __syncwarp();
@@ -469,9 +511,10 @@ __global__ void __launch_bounds__(NT + 32, MINB) stream_tile_kernel(const __grid
 
 // ---- launch plumbing shared by the library and by registering translation units ------------------------------
 
-constexpr int TILE_NT = 256;  // tile family: consumer threads = strip width
-constexpr int TILE_SR = 8;
-constexpr int TILE_NS = 3;
+// Tile-family geometries (measured on B200, tools/tune_stream.cu): wide strips and one CTA per SM for 3-row
+// windows, 256-column strips and two CTAs per SM otherwise.
+struct TileSmall { static constexpr int NT = 256, SR = 8, NS = 3, MAXCPS = 2; };
+struct TileBig { static constexpr int NT = 512, SR = 16, NS = 3, MAXCPS = 1; };
 
 struct LaunchGeom
 {
@@ -481,44 +524,64 @@ struct LaunchGeom
 };
 
 // Defined in kernels.cu: raises the kernel's dynamic shared-memory limit, asks the occupancy calculator how many
-// CTAs of `kernel` fit on an SM (an opaque user function may need any number of registers), splits the band
-// into work items accordingly and fills the item fields of `a`.
-LaunchGeom plan_stream_launch(StreamArgs& a, const void* kernel, int threads, size_t smem);
+// CTAs of `kernel` fit on an SM (an opaque user function may need any number of registers), caps that at
+// max_cps, splits the band into work items accordingly and fills the item fields of `a`.
+LaunchGeom plan_stream_launch(StreamArgs& a, const void* kernel, int threads, size_t smem, int max_cps);
 
-template <int MINB, class Op>
+// Fill the strip / pitch / stage fields of `a` for a tile-family geometry.
+template <class G>
+inline size_t tile_geometry(StreamArgs& a)
+{
+    a.TW = G::NT;
+    a.PW = a.Lp + a.TW + a.Rp;
+    a.nstrips = (a.b.nx + a.TW - 1) / a.TW;
+    a.PFX = a.b.V - 1;
+    a.stage_doubles = (a.PFX + G::SR) * a.PW;
+    return SMEM_STAGE_OFF + (size_t)G::NS * a.stage_doubles * sizeof(double);
+}
+
+template <class G, int MINB, class Op>
+inline void launch_tile_geom(StreamArgs& a, cudaStream_t st)
+{
+    auto kernel = stream_tile_kernel<G::NT, G::SR, G::NS, MINB, Op>;
+    const size_t smem = tile_geometry<G>(a);
+    const LaunchGeom g = plan_stream_launch(a, (const void*)kernel, G::NT + 32, smem, G::MAXCPS);
+    kernel<<<g.grid, g.threads, g.smem, st>>>(a);
+}
+
+// BIG selects the wide geometry when the window is at most 3 rows tall (its stages then fit in shared memory).
+template <bool BIG, int MINB, class Op>
 inline void launch_tile_instance(StreamArgs& a, cudaStream_t st)
 {
-    auto kernel = stream_tile_kernel<TILE_NT, TILE_SR, TILE_NS, MINB, Op>;
-    const size_t smem = SMEM_STAGE_OFF + (size_t)TILE_NS * a.stage_doubles * sizeof(double);
-    const LaunchGeom g = plan_stream_launch(a, (const void*)kernel, TILE_NT + 32, smem);
-    kernel<<<g.grid, g.threads, g.smem, st>>>(a);
+    if (BIG && a.b.V <= 3) launch_tile_geom<TileBig, 1, Op>(a, st);
+    else launch_tile_geom<TileSmall, MINB, Op>(a, st);
 }
 
 // Signature of a registered (inlined) launcher: picks the instance for the band's extents and launches it.
 typedef void (*InlineLauncher)(StreamArgs& a, cudaStream_t st);
 
-constexpr int INLINE_MINB = 3;  // inlined instances are compiled for three CTAs per SM
+constexpr int INLINE_MINB = 2;  // inlined instances are compiled for two CTAs per SM
 
 template <FunX F>
 inline void launch_inline_x(StreamArgs& a, cudaStream_t st)
 {
-    if (a.b.L == 1) launch_tile_instance<INLINE_MINB, OpInlineX<F, 1>>(a, st);
-    else if (a.b.L == 4) launch_tile_instance<INLINE_MINB, OpInlineX<F, 4>>(a, st);
-    else launch_tile_instance<INLINE_MINB, OpInlineX<F, -1>>(a, st);
+    if (a.b.L == 1) launch_tile_instance<false, INLINE_MINB, OpInlineX<F, 1>>(a, st);
+    else if (a.b.L == 4) launch_tile_instance<false, INLINE_MINB, OpInlineX<F, 4>>(a, st);
+    else launch_tile_instance<false, INLINE_MINB, OpInlineX<F, -1>>(a, st);
 }
 template <FunY F>
 inline void launch_inline_y(StreamArgs& a, cudaStream_t st)
 {
-    if (a.b.T == 1) launch_tile_instance<INLINE_MINB, OpInlineY<F, 1>>(a, st);
-    else if (a.b.T == 4) launch_tile_instance<INLINE_MINB, OpInlineY<F, 4>>(a, st);
-    else launch_tile_instance<INLINE_MINB, OpInlineY<F, -1>>(a, st);
+    if (a.b.T == 1) launch_tile_instance<false, INLINE_MINB, OpInlineY<F, 1>>(a, st);
+    else if (a.b.T == 4) launch_tile_instance<false, INLINE_MINB, OpInlineY<F, 4>>(a, st);
+    else launch_tile_instance<false, INLINE_MINB, OpInlineY<F, -1>>(a, st);
 }
 template <FunXY F>
 inline void launch_inline_xy(StreamArgs& a, cudaStream_t st)
 {
-    if (a.b.H == 3 && a.b.V == 3) launch_tile_instance<INLINE_MINB, OpInlineXY<F, 3, 3>>(a, st);
-    else if (a.b.H == 5 && a.b.V == 5) launch_tile_instance<INLINE_MINB, OpInlineXY<F, 5, 5>>(a, st);
-    else launch_tile_instance<INLINE_MINB, OpInlineXY<F, 0, 0>>(a, st);
+    if (a.b.H == 3 && a.b.V == 3) launch_tile_instance<true, INLINE_MINB, OpInlineXY<F, 3, 3>>(a, st);
+    else if (a.b.H == 5 && a.b.V == 5) launch_tile_instance<false, INLINE_MINB, OpInlineXY<F, 5, 5>>(a, st);
+    else launch_tile_instance<false, INLINE_MINB, OpInlineXY<F, 0, 0>>(a, st);
 }
 
 // Registry of inlined instances, keyed by the device address of the user function.
