@@ -37,7 +37,8 @@ EXPORTED = (
        "custen_last_path", "custen_last_mode", "custen_launch_count", "custen_set_tuning", "custen_set_slab",
        "custen_ipc_export", "custen_ipc_open", "custen_ipc_close", "custen_event_create", "custen_event_record",
        "custen_event_synchronize", "custen_event_elapsed_ms", "custen_event_destroy", "custen_host_alloc",
-       "custen_host_free", "custen_managed_alloc", "custen_managed_free"]
+       "custen_host_free", "custen_managed_alloc", "custen_managed_free", "custen_peer_barrier", "custen_device_alloc",
+       "custen_device_free"]
 )
 
 _lib = None
@@ -80,6 +81,10 @@ def load():
     lib.custen_event_destroy.argtypes, lib.custen_event_destroy.restype = [_c_void_p], None
     lib.custen_host_alloc.argtypes, lib.custen_host_alloc.restype = [ctypes.c_size_t], ctypes.c_void_p
     lib.custen_host_free.argtypes, lib.custen_host_free.restype = [_c_void_p], None
+    lib.custen_peer_barrier.argtypes = [_c_void_p, _c_void_p, _c_void_p, _c_void_p, ctypes.c_uint64]
+    lib.custen_peer_barrier.restype = None
+    lib.custen_device_alloc.argtypes, lib.custen_device_alloc.restype = [ctypes.c_size_t], ctypes.c_void_p
+    lib.custen_device_free.argtypes, lib.custen_device_free.restype = [_c_void_p], None
     lib.custen_managed_alloc.argtypes, lib.custen_managed_alloc.restype = [ctypes.c_size_t], ctypes.c_void_p
     lib.custen_managed_free.argtypes, lib.custen_managed_free.restype = [_c_void_p], None
     _lib = lib

@@ -171,6 +171,45 @@ void custen_ipc_close(void* mapped_ptr)
     checkError("cudaIpcCloseMemHandle");
 }
 
+// Neighbour barrier of the slab layer: one thread publishes this rank's epoch into the flag words of the slab
+// above and below (peer memory over NVLink) and spins until both neighbours have published theirs.  Ordered on
+// the handle's compute stream, so "my previous sweep is complete" is what the epoch announces.
+__global__ void custen_peer_barrier_kernel(unsigned long long* up_slot, unsigned long long* down_slot,
+                                           volatile unsigned long long* from_up, volatile unsigned long long* from_down,
+                                           unsigned long long epoch)
+{
+    __threadfence_system();
+    if (up_slot) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(up_slot), "l"(epoch) : "memory");
+    if (down_slot) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(down_slot), "l"(epoch) : "memory");
+    unsigned long long v;
+    if (up_slot)
+        do { asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(from_up) : "memory"); } while (v < epoch);
+    if (down_slot)
+        do { asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(from_down) : "memory"); } while (v < epoch);
+    __threadfence_system();
+}
+
+void custen_peer_barrier(cuSten_c_handle* h, void* up_flags, void* down_flags, void* my_flags, uint64_t epoch)
+{
+    // flag layout per rank: word 0 is written by the slab above, word 1 by the slab below
+    unsigned long long* mine = (unsigned long long*)my_flags;
+    unsigned long long* up = (unsigned long long*)up_flags;
+    unsigned long long* down = (unsigned long long*)down_flags;
+    custen_peer_barrier_kernel<<<1, 1, 0, H(h)->streams[0]>>>(up ? up + 1 : nullptr, down ? down + 0 : nullptr, mine + 0,
+                                                              mine + 1, (unsigned long long)epoch);
+    checkError("custen_peer_barrier");
+}
+
+void* custen_device_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    cudaMalloc(&p, bytes);
+    checkError("cudaMalloc");
+    cudaMemset(p, 0, bytes);
+    return p;
+}
+void custen_device_free(void* p) { cudaFree(p); }
+
 void* custen_event_create(void)
 {
     cudaEvent_t e;

@@ -115,6 +115,26 @@ class SlabStencil:
             top = peer_ptr(up) + (self.rows - self.T) * row if up is not None else 0
             bottom = peer_ptr(down) if down is not None else 0
             self.st.set_slab(top, bottom, first, last)
+            # neighbour barrier flags (2 x u64 per rank), exchanged the same way
+            self._flags = lib.custen_device_alloc(16)
+            fh = (ctypes.c_char * 64)()
+            lib.custen_ipc_export(self._flags, ctypes.addressof(fh), None)
+            fhandles = [None] * self.world
+            dist.all_gather_object(fhandles, bytes(fh), group=group)
+            fopened = {}
+
+            def flag_ptr(r):
+                if r is None:
+                    return None
+                if r not in fopened:
+                    buf = (ctypes.c_char * 64).from_buffer_copy(fhandles[r])
+                    fopened[r] = lib.custen_ipc_open(ctypes.addressof(buf))
+                    self._mapped.append(fopened[r])
+                return fopened[r]
+
+            self._up_flags, self._down_flags = flag_ptr(up), flag_ptr(down)
+            self._epoch = 0
+            dist.barrier(group=group)
         else:
             raise ValueError(transport)
 
@@ -124,11 +144,25 @@ class SlabStencil:
             if self.transport == "exchange" or self.world == 1:
                 exchange_halos(self.inp, self.T, self.B, self.top[: self.T], self.bottom[: self.B], self.rank,
                                self.world, self.periodic, self.group)
+            else:
+                # peer transport: the sweep reads the neighbours' edge rows in place, so all a step needs is to
+                # know that the neighbours have finished the previous one (and are done reading my rows)
+                from . import _lib
+                self._epoch += 1
+                _lib.load().custen_peer_barrier(ctypes.addressof(self.st.handle), self._up_flags, self._down_flags,
+                                                self._flags, self._epoch)
         self.st.compute(0)
 
     def destroy(self):
         from . import _lib
+        from .api import device_synchronize
+        device_synchronize()
+        if dist.is_initialized() and self.world > 1:
+            dist.barrier(group=self.group)  # nobody unmaps memory a neighbour may still be reading
         self.st.destroy()
         for p in self._mapped:
             _lib.load().custen_ipc_close(p)
         self._mapped = []
+        if getattr(self, "_flags", None):
+            _lib.load().custen_device_free(self._flags)
+            self._flags = None

@@ -102,6 +102,13 @@ void custen_ipc_export(const void* dev_ptr, void* handle64, size_t* offset_out);
 void* custen_ipc_open(const void* handle64);
 void custen_ipc_close(void* mapped_ptr);
 
+/* Neighbour barrier for the "peer" halo transport: flag words live in custen_device_alloc'ed memory (2 x u64 per
+ * rank, zero-initialised, exported with custen_ipc_export); up_flags / down_flags are the neighbours' mapped flag
+ * blocks (NULL where there is no neighbour).  Enqueued on the handle's compute stream. */
+void custen_peer_barrier(cuSten_c_handle* pt_cuSten, void* up_flags, void* down_flags, void* my_flags, uint64_t epoch);
+void* custen_device_alloc(size_t bytes);
+void custen_device_free(void* p);
+
 /* Event timing on the stream a handle launches on (streams[idx] of the handle). */
 void* custen_event_create(void);
 void custen_event_record(void* ev, cuSten_c_handle* pt_cuSten, int stream_idx);
