@@ -1,0 +1,38 @@
+"""Drop-in proof on the GPU: the reference's OWN example programs (examples/src/*.cu, compiled by oracle/Makefile from
+/root/reference against the reference's own cuSten.h) linked once against the reference library (<name>.ref) and once
+against this repo's libcuSten.a (<name>.new) must print the same thing.  The programs print every grid point
+(result, analytic answer, input), so this is an end-to-end comparison through the C++ API, unified memory, numTiles and
+the HOST offload path, including user __device__ functions device-linked across translation units."""
+import os
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXDIR = os.path.join(ROOT, "oracle", "_ref", "examples")
+EXAMPLES = ["2d_x_np", "2d_y_p", "2d_y_np", "2d_y_p_fun", "2d_y_np_fun", "2d_xy_np", "2d_xy_np_fun", "2d_xy_p"]
+
+
+@pytest.mark.parametrize("name", EXAMPLES)
+def test_reference_example_prints_the_same_with_the_new_library(name):
+    ref, new = os.path.join(EXDIR, name + ".ref"), os.path.join(EXDIR, name + ".new")
+    if not (os.path.exists(ref) and os.path.exists(new)):
+        pytest.skip("example binaries not built (need /root/reference at build time)")
+    a = subprocess.run([ref], capture_output=True, text=True, timeout=300)
+    b = subprocess.run([new], capture_output=True, text=True, timeout=300)
+    assert a.returncode == 0, a.stdout[-500:]
+    assert b.returncode == 0, b.stdout[-500:]
+    la, lb = a.stdout.splitlines(), b.stdout.splitlines()
+    assert len(la) == len(lb)
+    diff = [i for i, (x, y) in enumerate(zip(la, lb)) if x != y]
+    if name == "2d_y_np" and diff:
+        # reference defect: the bottom block row of kernel2DYnp is racy (2d_y_np_kernel.cu:229-241); lines are
+        # printed row by row, 512 per row, so only the last 8 rows (BLOCK_Y) may differ
+        assert min(diff) >= len(la) - 8 * 512
+        return
+    assert not diff, f"{len(diff)} of {len(la)} lines differ, first: {la[diff[0]]!r} vs {lb[diff[0]]!r}"
