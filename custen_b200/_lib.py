@@ -38,7 +38,8 @@ EXPORTED = (
        "custen_ipc_export", "custen_ipc_open", "custen_ipc_close", "custen_event_create", "custen_event_record",
        "custen_event_synchronize", "custen_event_elapsed_ms", "custen_event_destroy", "custen_host_alloc",
        "custen_host_free", "custen_managed_alloc", "custen_managed_free", "custen_peer_barrier", "custen_device_alloc",
-       "custen_device_free"]
+       "custen_device_free", "custen_cahn_create", "custen_cahn_set_field", "custen_cahn_step", "custen_cahn_get_field",
+       "custen_cahn_time_steps", "custen_cahn_destroy"]
 )
 
 _lib = None
@@ -85,6 +86,13 @@ def load():
     lib.custen_peer_barrier.restype = None
     lib.custen_device_alloc.argtypes, lib.custen_device_alloc.restype = [ctypes.c_size_t], ctypes.c_void_p
     lib.custen_device_free.argtypes, lib.custen_device_free.restype = [_c_void_p], None
+    lib.custen_cahn_create.argtypes = [_c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, _c_int]
+    lib.custen_cahn_create.restype = ctypes.c_void_p
+    lib.custen_cahn_set_field.argtypes, lib.custen_cahn_set_field.restype = [_c_void_p, _c_void_p], None
+    lib.custen_cahn_step.argtypes, lib.custen_cahn_step.restype = [_c_void_p, _c_int], None
+    lib.custen_cahn_get_field.argtypes, lib.custen_cahn_get_field.restype = [_c_void_p, _c_void_p], None
+    lib.custen_cahn_time_steps.argtypes, lib.custen_cahn_time_steps.restype = [_c_void_p, _c_int], ctypes.c_float
+    lib.custen_cahn_destroy.argtypes, lib.custen_cahn_destroy.restype = [_c_void_p], None
     lib.custen_managed_alloc.argtypes, lib.custen_managed_alloc.restype = [ctypes.c_size_t], ctypes.c_void_p
     lib.custen_managed_free.argtypes, lib.custen_managed_free.restype = [_c_void_p], None
     _lib = lib

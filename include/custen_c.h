@@ -123,6 +123,17 @@ void custen_host_free(void* p);
 void* custen_managed_alloc(size_t bytes);
 void custen_managed_free(void* p);
 
+/* Cahn-Hilliard ADI solver re-hosted on the engine (reference program cuPentCahnADI/src/cuPentCahnADI.cu and its
+ * timing twin cuPentSpeedUp/cuPentCahnADITiming/src/cuPentCahnADI.cu, whose main() this replaces):
+ * n x n periodic grid of side lx, dt = dt_over_dx * lx / n; the reference uses D = 1, gamma = 0.01, dt_over_dx = 0.1.
+ * set_field sets c(t=0) = c(t=-dt) like the reference's initial condition (cuPentCahnADI.cu:295-305). */
+void* custen_cahn_create(int nx, double D, double gamma, double lx, double dt_over_dx, int device);
+void custen_cahn_set_field(void* solver, const double* c0_host);
+void custen_cahn_step(void* solver, int nsteps);               /* asynchronous */
+void custen_cahn_get_field(void* solver, double* out_host);     /* synchronises */
+float custen_cahn_time_steps(void* solver, int nsteps);         /* milliseconds for nsteps steps (CUDA events) */
+void custen_cahn_destroy(void* solver);
+
 #ifdef __cplusplus
 }
 #endif

@@ -126,6 +126,81 @@ def ref_time(variant, nx, ny, coef, H=1, L=0, R=0, V=1, T=0, B=0, fun=None, tile
                         H, L, R, V, T, B, fun.encode() if fun else None, warmup, iters)
 
 
+_cahn_ref = None
+
+
+def ref_cahn_run(c0, nsteps, lx):
+    """The reference's GPU Cahn-Hilliard solver (timing twin + BatchHyper + cuPentBatch, oracle/ref_cahn_shim.cu):
+    returns (final field, ms per step)."""
+    global _cahn_ref
+    if _cahn_ref is None:
+        path = _ensure_built("libcahn_ref.so")
+        if path is None:
+            return None
+        _cahn_ref = ctypes.CDLL(path)
+        _cahn_ref.ref_cahn_run.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_double, _dp, _dp, _dp]
+        _cahn_ref.ref_cahn_run.restype = ctypes.c_int
+    c0 = np.ascontiguousarray(c0, dtype=np.float64)
+    n = c0.shape[0]
+    out = np.empty_like(c0)
+    ms = ctypes.c_double(0.0)
+    rc = _cahn_ref.ref_cahn_run(n, nsteps, lx, c0.ctypes.data_as(_dp), out.ctypes.data_as(_dp), ctypes.byref(ms))
+    assert rc == 0
+    return out, ms.value
+
+
+def serial_cahn_run(c0, nsteps, lx, D=1.0, gamma=0.01):
+    """The reference's serial CPU twin, driven function by function in the order of its own main loop
+    (serialCahnADI.c:1010-1047) from a caller-supplied field.  Returns the final field, or None if unavailable."""
+    lib = serial()
+    if lib is None:
+        return None
+    c0 = np.ascontiguousarray(c0, dtype=np.float64)
+    n = c0.shape[0]
+    m = n - 2
+    dx = lx / n
+    dt = 0.1 * dx
+    P = lambda a: a.ctypes.data_as(_dp)  # noqa: E731
+    dbl, cint = ctypes.c_double, ctypes.c_int
+    sig_l = 2.0 * dt * D * gamma / (3.0 * (dx * dx * dx * dx))
+    a, b, c, d, e = sig_l, -4 * sig_l, 1 + 6 * sig_l, -4 * sig_l, sig_l
+    ds, dl, diag, du, dw = (np.zeros(m) for _ in range(5))
+    lib.setLHS.argtypes = [_dp] * 5 + [dbl] * 5 + [cint]
+    lib.pentFactor.argtypes = [_dp] * 5 + [cint]
+    lib.findOmega.argtypes = [_dp] * 3 + [dbl] * 5 + [cint]
+    lib.findCBar.argtypes = [_dp] * 3 + [cint]
+    lib.findRHS.argtypes = [_dp] * 4 + [cint]
+    lib.cyclicInv.argtypes = [_dp] * 9 + [dbl] * 4 + [cint, cint]
+    lib.transpose.argtypes = [_dp, _dp, cint]
+    lib.findNew.argtypes = [_dp] * 3 + [cint]
+    for f in (lib.setLHS, lib.pentFactor, lib.findOmega, lib.findCBar, lib.findRHS, lib.cyclicInv, lib.transpose, lib.findNew):
+        f.restype = None
+    lib.setLHS(P(ds), P(dl), P(diag), P(du), P(dw), a, b, c, d, e, m)
+    lib.pentFactor(P(ds), P(dl), P(diag), P(du), P(dw), m)
+    omega, inv1, inv2 = np.zeros(4), np.zeros(m), np.zeros(m)
+    lib.findOmega(P(omega), P(inv1), P(inv2), a, b, c, d, e, m)
+    w_lin = np.array([0, 0, -1, 0, 0, 0, -2, 8, -2, 0, -1, 8, -20, 8, -1, 0, -2, 8, -2, 0, 0, 0, -1, 0, 0], dtype=np.float64) * sig_l
+    sig_n = (dt / 3.0) * D * (2.0 / (dx * dx))
+    w_non = np.array([0, 1, 0, 1, -4, 1, 0, 1, 0], dtype=np.float64) * sig_n
+    c_old, c_cur = c0.copy(), c0.copy()
+    c_bar, c_half, c_non = np.zeros_like(c0), np.zeros_like(c0), np.zeros_like(c0)
+    for _ in range(nsteps):
+        lib.findCBar(P(c_old), P(c_cur), P(c_bar), n)
+        lib.linearRHS(P(c_bar), P(c_half), P(w_lin), 5, 5, 2, 2, n)
+        lib.nonlinearRHS(P(c_cur), P(c_non), P(w_non), 3, 3, 1, 1, n)
+        lib.findRHS(P(c_old), P(c_cur), P(c_half), P(c_non), n)
+        for i in range(n):
+            row = ctypes.cast(c_half.ctypes.data + i * n * 8, _dp)
+            lib.cyclicInv(P(ds), P(dl), P(diag), P(du), P(dw), P(inv1), P(inv2), P(omega), row, a, b, d, e, m, n)
+        lib.transpose(P(c_half), P(c_cur), n)
+        for i in range(n):
+            row = ctypes.cast(c_cur.ctypes.data + i * n * 8, _dp)
+            lib.cyclicInv(P(ds), P(dl), P(diag), P(du), P(dw), P(inv1), P(inv2), P(omega), row, a, b, d, e, m, n)
+        lib.transpose(P(c_cur), P(c_half), n)
+        lib.findNew(P(c_cur), P(c_bar), P(c_half), n)
+    return c_cur
+
+
 def bits_equal(a, b):
     return np.array_equal(np.ascontiguousarray(a).view(np.int64), np.ascontiguousarray(b).view(np.int64))
 

@@ -1,0 +1,78 @@
+"""BASELINE.json config 5: the Cahn-Hilliard ADI solver re-hosted on the new engine, against (a) the reference's own
+GPU solver (timing twin + BatchHyper + cuPentBatch rebuilt for sm_100) — bit for bit, the operation order is kept —
+and (b) the reference's serial CPU twin (built without FMA, so: to rounding)."""
+import math
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+from custen_b200.cahn import CahnHilliard  # noqa: E402
+
+LX = 16.0 * math.pi
+
+
+def _initial(n, seed=0):
+    return np.random.default_rng(seed).uniform(-0.1, 0.1, size=(n, n))
+
+
+def _ours(c0, nsteps, lx=LX):
+    s = CahnHilliard(c0.shape[0], lx=lx)
+    s.set_field(c0)
+    s.step(nsteps)
+    out = s.field()
+    s.destroy()
+    return out
+
+
+@pytest.mark.parametrize("n,steps", [(64, 5), (256, 25), (512, 10)])
+def test_bit_exact_against_reference_gpu_solver(n, steps):
+    c0 = _initial(n, seed=n)
+    ref = ol.ref_cahn_run(c0, steps, LX)
+    if ref is None:
+        pytest.skip("reference GPU solver not built")
+    ref_field, _ = ref
+    got = _ours(c0, steps)
+    diff = ol.count_diff(got, ref_field)
+    rel = np.max(np.abs(got - ref_field)) / np.max(np.abs(ref_field))
+    assert rel < 1e-13, rel
+    assert diff == 0, f"{diff} points differ (max rel {rel:.3e})"
+
+
+@pytest.mark.parametrize("n,steps", [(64, 10), (128, 20)])
+def test_against_reference_serial_cpu_twin(n, steps):
+    c0 = _initial(n, seed=7 * n)
+    want = ol.serial_cahn_run(c0, steps, LX)
+    if want is None:
+        pytest.skip("reference serial twin not built")
+    got = _ours(c0, steps)
+    rel = np.max(np.abs(got - want)) / np.max(np.abs(want))
+    assert rel < 1e-11, rel
+
+
+def test_mass_is_conserved_at_full_size():
+    """Size-independent property at the BASELINE size (4096^2): the scheme conserves the mean of c."""
+    n = 4096
+    c0 = _initial(n, seed=1)
+    got = _ours(c0, 10)
+    assert np.isfinite(got).all()
+    assert abs(got.mean() - c0.mean()) < 1e-13
+    assert 0.0 < np.abs(got).max() < 0.2
+
+
+def test_steps_compose():
+    c0 = _initial(128, seed=3)
+    a = _ours(c0, 12)
+    s = CahnHilliard(128)
+    s.set_field(c0)
+    for _ in range(4):
+        s.step(3)
+    b = s.field()
+    s.destroy()
+    assert ol.count_diff(a, b) == 0
