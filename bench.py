@@ -358,6 +358,20 @@ def run_ours(args, rank, world, local_rank):
             s2.destroy()
             del a, b
 
+    if world == 1 and not args.no_table:
+        # BASELINE.json config 5 (and the 512^2 size of config 1): Cahn-Hilliard ADI steps on the re-hosted solver
+        from custen_b200.cahn import CahnHilliard
+        for ncahn in (512, 4096):
+            sol = CahnHilliard(ncahn, device=local_rank)
+            sol.set_field(np.random.default_rng(0).uniform(-0.1, 0.1, (ncahn, ncahn)))
+            sol.step(3)
+            ms_step = sol.time_steps(20)
+            sol.destroy()
+            extras[f"cahn_hilliard_{ncahn}"] = {"ms_per_step": round(ms_step, 4),
+                                               "mpoint_steps_per_s": round(ncahn * ncahn / ms_step / 1e3, 1),
+                                               "note": "custen_cahn_step: 2 stencils + 2 cyclic pentadiagonal ADI solves per step, "
+                                                       "bit-identical to the reference GPU solver (tests/test_cahn_gpu.py)"}
+
     cpu = None
     if world == 1 and not args.no_cpu:
         try:
@@ -371,6 +385,24 @@ def run_ours(args, rank, world, local_rank):
                              f"(serialCahnADI.c:553-622), {t:.1f} s on 1 of {len(os.sched_getaffinity(0))} host threads"}
         except Exception as ex:  # the oracle is a checker; its absence must not hide the GPU numbers
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"unavailable: {ex}"}
+        # BASELINE.json config 1: the reference's serial CPU Cahn-Hilliard program, 512^2, as shipped (T = 10)
+        exe = os.path.join(ROOT, "oracle", "_ref", "serialCahnADI")
+        if os.path.exists(exe) and not args.no_serial:
+            try:
+                r = subprocess.run([exe, "512"], capture_output=True, text=True, timeout=240)
+                secs = float(r.stdout.split()[0])
+                nsteps = 0
+                t, dt = 0.0, 0.1 * (16.0 * np.pi / 512)
+                while t < 10.0:  # the program's own loop condition (serialCahnADI.c:1010)
+                    t += dt
+                    nsteps += 1
+                extras["config1_serial_cpu_cahn_512"] = {
+                    "seconds": secs, "steps": nsteps, "mpoint_steps_per_s": round(512 * 512 * nsteps / secs / 1e6, 2),
+                    "cores": 1, "host_threads_available": len(os.sched_getaffinity(0)),
+                    "note": "oracle/_ref/serialCahnADI 512 = cuPentSpeedUp/serialCahnADITiming/serialCahnADI.c built as "
+                            "compile.sh:18 minus the unused HDF5 flags; its own clock() print"}
+            except Exception as ex:
+                extras["config1_serial_cpu_cahn_512"] = {"error": str(ex)}
 
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -407,12 +439,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="xy_p_fun_32768", choices=sorted(WORKLOADS))
-    ap.add_argument("--transport", default="exchange", choices=["exchange", "peer"])
+    ap.add_argument("--transport", default="peer", choices=["exchange", "peer"],
+                    help="halo transport at N > 1: 'peer' reads the neighbours' edge rows in place over NVLink (IPC), "
+                         "'exchange' sends them with NCCL every step")
     ap.add_argument("--e2e-tiles", type=int, default=8)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-table", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-serial", action="store_true", help="skip the ~30 s serial CPU Cahn-Hilliard baseline (config 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     rank = int(os.environ.get("RANK", "0"))

@@ -34,6 +34,13 @@ def main(out, n):
     ms = ol.ref_time("XYpFun", n, n, coef, tiles=1, block=(8, 8), warmup=3, iters=10, **kw)
     res["rows"]["XYpFun_8x8"] = {"block": (8, 8), "ms": ms, "gpoints_per_s": n * n / ms / 1e6}
     print("XYpFun_8x8", res["rows"]["XYpFun_8x8"], flush=True)
+    # config 5: the reference's GPU Cahn-Hilliard solver, ms per step
+    for ncahn, steps in ((512, 20), (4096, 5)):
+        c0 = np.random.default_rng(0).uniform(-0.1, 0.1, (ncahn, ncahn))
+        r = ol.ref_cahn_run(c0, steps, 16 * np.pi)
+        if r is not None:
+            res["rows"][f"cahn_hilliard_{ncahn}"] = {"ms_per_step": r[1], "mpoint_steps_per_s": ncahn * ncahn / r[1] / 1e3}
+            print("cahn", ncahn, res["rows"][f"cahn_hilliard_{ncahn}"], flush=True)
     json.dump(res, open(out, "w"), indent=1)
 
 
