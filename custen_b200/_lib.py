@@ -32,7 +32,7 @@ _CREATE_TAIL = {
 
 # every symbol include/custen_c.h declares (tests check the library exports all of them)
 EXPORTED = (
-    [f"custen{op}2D{v}" for v in VARIANTS for op in ("Create", "Swap", "Destroy", "Compute")]
+    [f"custen{op}2D{v}" for v in VARIANTS + ("XYWENOADVp",) for op in ("Create", "Swap", "Destroy", "Compute")]
     + ["custenCheckError", "custen_handle_size", "custen_device_synchronize", "custen_builtin_fun",
        "custen_last_path", "custen_last_mode", "custen_launch_count", "custen_set_tuning", "custen_set_slab",
        "custen_ipc_export", "custen_ipc_open", "custen_ipc_close", "custen_event_create", "custen_event_record",
@@ -63,6 +63,12 @@ def load():
         f.argtypes, f.restype = [_c_void_p], None
         f = getattr(lib, f"custenCompute2D{v}")
         f.argtypes, f.restype = [_c_void_p, _c_int], None
+    f = lib.custenCreate2DXYWENOADVp
+    f.argtypes = [_c_void_p] + [_c_int] * 6 + [ctypes.c_double, ctypes.c_double] + [_c_dbl_p] * 4
+    f.restype = None
+    lib.custenSwap2DXYWENOADVp.argtypes, lib.custenSwap2DXYWENOADVp.restype = [_c_void_p, _c_dbl_p], None
+    lib.custenDestroy2DXYWENOADVp.argtypes, lib.custenDestroy2DXYWENOADVp.restype = [_c_void_p], None
+    lib.custenCompute2DXYWENOADVp.argtypes, lib.custenCompute2DXYWENOADVp.restype = [_c_void_p, _c_int], None
     lib.custenCheckError.argtypes, lib.custenCheckError.restype = [ctypes.c_char_p], None
     lib.custen_handle_size.argtypes, lib.custen_handle_size.restype = [], ctypes.c_size_t
     lib.custen_device_synchronize.argtypes, lib.custen_device_synchronize.restype = [], None

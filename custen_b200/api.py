@@ -86,6 +86,24 @@ for _v in _lib.VARIANTS:
 del _v, _c, _k, _s, _d
 
 
+def cuStenCreate2DXYWENOADVp(handle, deviceNum, numTiles, nx, ny, BLOCK_X, BLOCK_Y, dx, dy, u, v, dataOutput, dataInput):
+    """13th variant: periodic fifth-order WENO advection u dphi/dx + v dphi/dy (cuSten_struct_functions.h:309)."""
+    _lib.load().custenCreate2DXYWENOADVp(_h(handle), deviceNum, numTiles, nx, ny, BLOCK_X, BLOCK_Y, float(dx), float(dy),
+                                         ptr(u), ptr(v), ptr(dataOutput), ptr(dataInput))
+
+
+def cuStenCompute2DXYWENOADVp(handle, offload):
+    _lib.load().custenCompute2DXYWENOADVp(_h(handle), int(offload))
+
+
+def cuStenSwap2DXYWENOADVp(handle, dataInput):
+    _lib.load().custenSwap2DXYWENOADVp(_h(handle), ptr(dataInput))
+
+
+def cuStenDestroy2DXYWENOADVp(handle):
+    _lib.load().custenDestroy2DXYWENOADVp(_h(handle))
+
+
 def checkError(action):
     _lib.load().custenCheckError(action.encode())
 

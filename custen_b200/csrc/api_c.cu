@@ -70,6 +70,13 @@ void custenCreate2DXYnpFun(PFX, double* c, int hh, int l, int r, int vv, int t, 
 }
 C_COMMON(XYnpFun)
 
+void custenCreate2DXYWENOADVp(cuSten_c_handle* h, int dev, int tiles, int nx, int ny, int bx, int by, double dx, double dy,
+                              double* u, double* v, double* out, double* in)
+{
+    cuStenCreate2DXYWENOADVp(H(h), dev, tiles, nx, ny, bx, by, dx, dy, u, v, out, in);
+}
+C_COMMON(XYWENOADVp)
+
 void custenCheckError(const char* action) { checkError(action); }
 
 // ---- additive -------------------------------------------------------------------------------------------------

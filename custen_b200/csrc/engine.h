@@ -36,6 +36,11 @@ struct Band
     int xlo, xhi;          // columns written: xlo <= x < xhi
     int ylo, yhi;          // band-local rows written: ylo <= y < yhi
     int zero_right;        // Xnp quirk (2d_x_np_kernel.cu:164-176): columns x >= xhi receive 0.0
+    // WENO advection variant only (2d_xyADVWENO_p_kernel.cu): velocities (same row pitch as `out`) and 1/dx, 1/dy
+    const double* aux0;
+    const double* aux1;
+    double p0, p1;
+    int weno;
 };
 
 // Which kernel family served a launch (reported through the C ABI for tests / bench).

@@ -33,7 +33,7 @@ namespace custen {
 constexpr int FB_BX = 32;
 constexpr int FB_BY = 8;
 
-// MODE: 0 weights, 1 FunX, 2 FunY, 3 FunXY
+// MODE: 0 weights, 1 FunX, 2 FunY, 3 FunXY, 4 WENO advection
 template <int MODE>
 __global__ void __launch_bounds__(FB_BX* FB_BY) fallback_kernel(const __grid_constant__ Band b)
 {
@@ -84,7 +84,8 @@ __global__ void __launch_bounds__(FB_BX* FB_BY) fallback_kernel(const __grid_con
     }
     else if (MODE == 1) sum = ((FunX)b.func)(tile, cf, tl + b.L);
     else if (MODE == 2) sum = ((FunY)b.func)(tile, cf, tl + b.T * PW, PW);
-    else sum = ((FunXY)b.func)(tile, cf, tl, PW, b.H, b.V);
+    else if (MODE == 3) sum = ((FunXY)b.func)(tile, cf, tl, PW, b.H, b.V);
+    else sum = OpWeno::apply(b, tile, cf, tl, PW, (ptrdiff_t)y * b.nx + x);
     *o = sum;
 }
 
@@ -124,7 +125,7 @@ static int launch_fallback(const Band& b, cudaStream_t st)
     const int Reff = b.H - 1 - b.L, Beff = b.V - 1 - b.T;
     const size_t smem = ((size_t)(FB_BX + b.L + Reff) * (FB_BY + b.T + Beff) + b.ncoef) * sizeof(double);
     dim3 grid((b.nx + FB_BX - 1) / FB_BX, (b.rows + FB_BY - 1) / FB_BY), block(FB_BX, FB_BY);
-    const int mode = b.func ? (b.dir == DIR_X ? 1 : b.dir == DIR_Y ? 2 : 3) : 0;
+    const int mode = b.weno ? 4 : b.func ? (b.dir == DIR_X ? 1 : b.dir == DIR_Y ? 2 : 3) : 0;
 #define FB_CASE(M)                                                                                          \
     case M:                                                                                                 \
         if (smem > 48 * 1024)                                                                               \
@@ -133,7 +134,7 @@ static int launch_fallback(const Band& b, cudaStream_t st)
         break;
     switch (mode)
     {
-        FB_CASE(0) FB_CASE(1) FB_CASE(2) FB_CASE(3)
+        FB_CASE(0) FB_CASE(1) FB_CASE(2) FB_CASE(3) FB_CASE(4)
     }
 #undef FB_CASE
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -252,6 +253,11 @@ int launch_band(const Band& b, cudaStream_t st)
     a.Rp = round_even(Reff);
     a.Beff = Beff;
 
+    if (b.weno)
+    {
+        launch_tile_instance<false, 2, OpWeno>(a, st);
+        return PATH_STREAM_TILE;
+    }
     const bool lodd = (b.L & 1) != 0;
     if (!b.func && !tu.force_tile)
     {

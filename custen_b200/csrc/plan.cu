@@ -20,7 +20,8 @@ static void check(const char* what, int device)
 Plan* plan_of(cuSten_t* h)
 {
     if (!h || !h->streams) return nullptr;
-    uintptr_t* tail = reinterpret_cast<uintptr_t*>(h->streams + 3);
+    if (h->numStreams < 3 || h->numStreams > 16) return nullptr;
+    uintptr_t* tail = reinterpret_cast<uintptr_t*>(h->streams + h->numStreams);
     if (tail[0] != kMagic) return nullptr;
     return reinterpret_cast<Plan*>(tail[1]);
 }
@@ -52,13 +53,13 @@ static void set_boundaries(cuSten_t* h, double* base)
     }
 }
 
-void plan_create(cuSten_t* h, Spec spec, int deviceNum, int numTiles, int nx, int ny, int BLOCK_X, int BLOCK_Y,
-                 double* dataOutput, double* dataInput, double* coef, int H, int L, int R, int V, int T, int B,
-                 int numCoe, double* func)
+static void plan_create_impl(cuSten_t* h, Spec spec, int nstreams, int deviceNum, int numTiles, int nx, int ny, int BLOCK_X,
+                             int BLOCK_Y, double* dataOutput, double* dataInput, double* coef, int H, int L, int R, int V,
+                             int T, int B, int numCoe, double* func)
 {
     memset(h, 0, sizeof *h);
     h->deviceNum = deviceNum;
-    h->numStreams = 3;
+    h->numStreams = nstreams;
     h->numTiles = numTiles < 1 ? 1 : numTiles;
     h->nx = nx;
     h->ny = ny;
@@ -68,9 +69,9 @@ void plan_create(cuSten_t* h, Spec spec, int deviceNum, int numTiles, int nx, in
     cudaSetDevice(deviceNum);
     check("Setting current device", deviceNum);
 
-    // three public streams (blocking, like the reference's cudaStreamCreate) + hidden tail
-    h->streams = (cudaStream_t*)calloc(3 + 2, sizeof(cudaStream_t));
-    for (int s = 0; s < 3; ++s)
+    // the public streams (blocking, like the reference's cudaStreamCreate; 3, or 6 for WENO) + hidden tail
+    h->streams = (cudaStream_t*)calloc(nstreams + 2, sizeof(cudaStream_t));
+    for (int s = 0; s < nstreams; ++s)
     {
         cudaStreamCreate(&h->streams[s]);
         check("Creating stream", deviceNum);
@@ -84,7 +85,7 @@ void plan_create(cuSten_t* h, Spec spec, int deviceNum, int numTiles, int nx, in
 
     Plan* p = (Plan*)calloc(1, sizeof(Plan));
     p->spec = spec;
-    uintptr_t* tail = reinterpret_cast<uintptr_t*>(h->streams + 3);
+    uintptr_t* tail = reinterpret_cast<uintptr_t*>(h->streams + nstreams);
     tail[0] = kMagic;
     tail[1] = reinterpret_cast<uintptr_t>(p);
 
@@ -133,6 +134,36 @@ void plan_create(cuSten_t* h, Spec spec, int deviceNum, int numTiles, int nx, in
     }
 }
 
+void plan_create(cuSten_t* h, Spec spec, int deviceNum, int numTiles, int nx, int ny, int BLOCK_X, int BLOCK_Y,
+                 double* dataOutput, double* dataInput, double* coef, int H, int L, int R, int V, int T, int B,
+                 int numCoe, double* func)
+{
+    plan_create_impl(h, spec, 3, deviceNum, numTiles, nx, ny, BLOCK_X, BLOCK_Y, dataOutput, dataInput, coef, H, L, R, V, T, B,
+                     numCoe, func);
+}
+
+// 13th variant: periodic WENO5 advection, fixed 7 x 7 cross (custenCreateDestroy2DXYADVWENOp.cu:57-264): six public
+// streams, 1/dx and 1/dy in coeDx / coeDy, per-tile aliases into the two velocity arrays.
+void plan_create_weno(cuSten_t* h, int deviceNum, int numTiles, int nx, int ny, int BLOCK_X, int BLOCK_Y, double dx,
+                      double dy, double* u, double* v, double* dataOutput, double* dataInput)
+{
+    plan_create_impl(h, Spec{DIR_XY, 1, 0, 1}, 6, deviceNum, numTiles, nx, ny, BLOCK_X, BLOCK_Y, dataOutput, dataInput,
+                     nullptr, 7, 3, 3, 7, 3, 3, 0, nullptr);
+    h->coeDx = 1.0 / dx;
+    h->coeDy = 1.0 / dy;
+    h->uVel = (double**)calloc(h->numTiles, sizeof(double*));
+    h->vVel = (double**)calloc(h->numTiles, sizeof(double*));
+    const ptrdiff_t off = (ptrdiff_t)nx * h->nyTile;
+    for (int t = 0; t < h->numTiles; ++t)
+    {
+        h->uVel[t] = u + t * off;
+        h->vVel[t] = v + t * off;
+    }
+    Plan* p = plan_of(h);
+    p->ncoef = 0;
+    h->mem_shared = (int)(((size_t)h->nxLocal * h->nyLocal + h->numSten) * sizeof(double));
+}
+
 void plan_swap(cuSten_t* h, double* dataInput)
 {
     for (int t = 0; t < h->numTiles; ++t) std::swap(h->dataInput[t], h->dataOutput[t]);
@@ -174,7 +205,7 @@ void plan_destroy(cuSten_t* h)
         release_staging(p);
         free(p);
     }
-    for (int s = 0; s < h->numStreams && s < 3; ++s)
+    for (int s = 0; s < h->numStreams; ++s)
     {
         cudaStreamDestroy(h->streams[s]);
         check("Destroying stream", h->deviceNum);
@@ -190,6 +221,9 @@ void plan_destroy(cuSten_t* h)
     free(h->dataOutput);
     free(h->boundaryTop);
     free(h->boundaryBottom);
+    free(h->uVel);
+    free(h->vVel);
+    h->uVel = h->vVel = nullptr;
     h->streams = nullptr;
     h->events = nullptr;
     h->dataInput = h->dataOutput = h->boundaryTop = h->boundaryBottom = nullptr;
@@ -234,6 +268,14 @@ static Band make_band(const cuSten_t* h, const Plan* p, const double* coef, int 
     const int n = h->numTiles;
     b.in = h->dataInput[first_tile];
     b.out = h->dataOutput[first_tile];
+    if (s.weno)
+    {
+        b.weno = 1;
+        b.aux0 = h->uVel[first_tile];
+        b.aux1 = h->vVel[first_tile];
+        b.p0 = h->coeDx;
+        b.p1 = h->coeDy;
+    }
     b.rows = h->nyTile * (last_tile - first_tile + 1);
     b.ylo = 0;
     b.yhi = b.rows;
@@ -275,6 +317,7 @@ static bool tiles_contiguous(const cuSten_t* h)
             if (h->boundaryTop[t] != h->dataInput[t] - (ptrdiff_t)h->numStenTop * h->nx) return false;
             if (h->boundaryBottom[t - 1] != h->dataInput[t]) return false;
         }
+        if (h->uVel && (h->uVel[t] != h->uVel[0] + t * off || h->vVel[t] != h->vVel[0] + t * off)) return false;
     }
     return true;
 }
@@ -323,6 +366,11 @@ static void prefetch_tile(cuSten_t* h, int t, int dst, cudaStream_t st)
     const size_t tile_bytes = (size_t)h->nx * h->nyTile * sizeof(double);
     prefetch(h->dataInput[t], tile_bytes, dst, st);
     prefetch(h->dataOutput[t], tile_bytes, dst, st);
+    if (h->uVel)
+    {
+        prefetch(h->uVel[t], tile_bytes, dst, st);
+        prefetch(h->vVel[t], tile_bytes, dst, st);
+    }
     if (h->boundaryTop)
     {
         prefetch(h->boundaryTop[t], (size_t)h->numBoundaryTop * sizeof(double), dst, st);
@@ -464,7 +512,13 @@ void plan_compute(cuSten_t* h, bool offload)
     const double* coef = s.fun ? h->coe : h->weights;
     const MemKind kin = classify(h->dataInput[0]);
     const MemKind kout = classify(h->dataOutput[0]);
-    MemKind kcoef = classify(coef);
+    MemKind kcoef = coef ? classify(coef) : MK_DEVICE;
+    if (s.weno && (kin == MK_HOST || kout == MK_HOST || classify(h->uVel[0]) == MK_HOST || classify(h->vVel[0]) == MK_HOST))
+    {
+        printf("\ncuSten: the WENO variant needs device or unified memory buffers (host staging is not implemented for it)\n"
+               "program terminated ...\n\n");
+        exit(EXIT_FAILURE);
+    }
 
     // coefficients living in plain host memory are snapshotted to the device, stream-ordered
     if (kcoef == MK_HOST)

@@ -17,13 +17,14 @@ struct Spec
     int dir;        // Dir
     int periodic;   // 1 periodic, 0 non-periodic
     int fun;        // 1 function-pointer variant
+    int weno;       // 1 WENO advection variant (cuStenCreate2DXYWENOADVp)
 };
 
 enum MemKind : int { MK_DEVICE = 0, MK_MANAGED = 1, MK_HOST = 2 };
 
 constexpr int kSlots = 3;  // staging ring depth for host-resident grids
 
-// Private state hung behind the public `streams` array (slot 3 = magic, slot 4 = Plan*), so that
+// Private state hung behind the public `streams` array (slot numStreams = magic, the next = Plan*), so that
 // sizeof(cuSten_t) and every public field offset stay as in the reference.
 struct Plan
 {
@@ -50,6 +51,8 @@ Plan* plan_of(cuSten_t* h);
 void plan_create(cuSten_t* h, Spec spec, int deviceNum, int numTiles, int nx, int ny, int BLOCK_X, int BLOCK_Y,
                  double* dataOutput, double* dataInput, double* coef, int H, int L, int R, int V, int T, int B,
                  int numCoe, double* func);
+void plan_create_weno(cuSten_t* h, int deviceNum, int numTiles, int nx, int ny, int BLOCK_X, int BLOCK_Y, double dx,
+                      double dy, double* u, double* v, double* dataOutput, double* dataInput);
 void plan_swap(cuSten_t* h, double* dataInput);
 void plan_destroy(cuSten_t* h);
 void plan_compute(cuSten_t* h, bool offload);

@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(NT + 32, MINB) stream_acc_kernel(const __grid_
 
 struct OpWeights  // run-time H x V weights (shapes without a register-accumulator instance)
 {
-    static __device__ __forceinline__ double apply(const Band& b, double* buf, double* cf, int tl, int PW)
+    static __device__ __forceinline__ double apply(const Band& b, double* buf, double* cf, int tl, int PW, ptrdiff_t gidx)
     {
         double sum = 0.0;
         for (int j = 0; j < b.V; ++j)
@@ -386,21 +386,21 @@ struct OpWeights  // run-time H x V weights (shapes without a register-accumulat
 };
 struct OpPtrX  // opaque device pointer, X contract: loc = centre
 {
-    static __device__ __forceinline__ double apply(const Band& b, double* buf, double* cf, int tl, int PW)
+    static __device__ __forceinline__ double apply(const Band& b, double* buf, double* cf, int tl, int PW, ptrdiff_t gidx)
     {
         return ((FunX)b.func)(buf, cf, tl + b.L);
     }
 };
 struct OpPtrY  // loc = centre, jump = pitch
 {
-    static __device__ __forceinline__ double apply(const Band& b, double* buf, double* cf, int tl, int PW)
+    static __device__ __forceinline__ double apply(const Band& b, double* buf, double* cf, int tl, int PW, ptrdiff_t gidx)
     {
         return ((FunY)b.func)(buf, cf, tl + b.T * PW, PW);
     }
 };
 struct OpPtrXY  // loc = TOP-LEFT of the window (2d_xy_p_fun_kernel.cu:521)
 {
-    static __device__ __forceinline__ double apply(const Band& b, double* buf, double* cf, int tl, int PW)
+    static __device__ __forceinline__ double apply(const Band& b, double* buf, double* cf, int tl, int PW, ptrdiff_t gidx)
     {
         return ((FunXY)b.func)(buf, cf, tl, PW, b.H, b.V);
     }
@@ -410,7 +410,7 @@ struct OpPtrXY  // loc = TOP-LEFT of the window (2d_xy_p_fun_kernel.cu:521)
 template <FunX F, int LC>
 struct OpInlineX
 {
-    static __device__ __forceinline__ double apply(const Band& b, double* buf, double* cf, int tl, int PW)
+    static __device__ __forceinline__ double apply(const Band& b, double* buf, double* cf, int tl, int PW, ptrdiff_t gidx)
     {
         return F(buf, cf, tl + (LC >= 0 ? LC : b.L));
     }
@@ -418,7 +418,7 @@ struct OpInlineX
 template <FunY F, int TC>
 struct OpInlineY
 {
-    static __device__ __forceinline__ double apply(const Band& b, double* buf, double* cf, int tl, int PW)
+    static __device__ __forceinline__ double apply(const Band& b, double* buf, double* cf, int tl, int PW, ptrdiff_t gidx)
     {
         return F(buf, cf, tl + (TC >= 0 ? TC : b.T) * PW, PW);
     }
@@ -426,9 +426,64 @@ struct OpInlineY
 template <FunXY F, int HC, int VC>
 struct OpInlineXY
 {
-    static __device__ __forceinline__ double apply(const Band& b, double* buf, double* cf, int tl, int PW)
+    static __device__ __forceinline__ double apply(const Band& b, double* buf, double* cf, int tl, int PW, ptrdiff_t gidx)
     {
         return F(buf, cf, tl, PW, HC > 0 ? HC : b.H, VC > 0 ? VC : b.V);
+    }
+};
+
+// Fifth-order WENO advection u dphi/dx + v dphi/dy, upwinded per point (13th public variant).  The expressions are
+// those of the reference (2d_xyADVWENO_p_kernel.cu:51-86, :283-390; notation of Osher & Fedkiw, Level Set Methods),
+// including its use of the single-precision powf on double arguments, so that results match it bit for bit.
+__device__ __forceinline__ double weno5(double v1, double v2, double v3, double v4, double v5)
+{
+    const double epsilon = 1e-06;
+    const double phi1 = (1.0 / 3.0) * v1 - (7.0 / 6.0) * v2 + (11.0 / 6.0) * v3;
+    const double phi2 = -(1.0 / 6.0) * v2 + (5.0 / 6.0) * v3 + (1.0 / 3.0) * v4;
+    const double phi3 = (1.0 / 3.0) * v3 + (5.0 / 6.0) * v4 - (1.0 / 6.0) * v5;
+    const double s1 = (13.0 / 12.0) * powf(v1 - 2.0 * v2 + v3, 2.0) + 0.25 * powf(v1 - 4.0 * v2 + 3.0 * v3, 2.0);
+    const double s2 = (13.0 / 12.0) * powf(v2 - 2.0 * v3 + v4, 2.0) + 0.25 * powf(v2 - v4, 2.0);
+    const double s3 = (13.0 / 12.0) * powf(v3 - 2.0 * v4 + v5, 2.0) + 0.25 * powf(3.0 * v3 - 4.0 * v4 + v5, 2.0);
+    const double alpha1 = 0.1 / powf(s1 + epsilon, 2.0);
+    const double alpha2 = 0.6 / powf(s2 + epsilon, 2.0);
+    const double alpha3 = 0.3 / powf(s3 + epsilon, 2.0);
+    const double denom = 1.0 / (alpha1 + alpha2 + alpha3);
+    const double w1 = alpha1 * denom;
+    const double w2 = alpha2 * denom;
+    const double w3 = alpha3 * denom;
+    return phi1 * w1 + phi2 * w2 + phi3 * w3;
+}
+// one-sided differences along a line through the centre; `c` = centre index, `st` = element stride of the line
+__device__ __forceinline__ double weno_line(const double* a, int c, int st, double vel, double coe)
+{
+    double v1, v2, v3, v4, v5;
+    if (vel > 0.0)
+    {
+        v1 = (a[c - 2 * st] - a[c - 3 * st]) * coe;
+        v2 = (a[c - st] - a[c - 2 * st]) * coe;
+        v3 = (a[c] - a[c - st]) * coe;
+        v4 = (a[c + st] - a[c]) * coe;
+        v5 = (a[c + 2 * st] - a[c + st]) * coe;
+    }
+    else
+    {
+        v5 = (a[c - st] - a[c - 2 * st]) * coe;
+        v4 = (a[c] - a[c - st]) * coe;
+        v3 = (a[c + st] - a[c]) * coe;
+        v2 = (a[c + 2 * st] - a[c + st]) * coe;
+        v1 = (a[c + 3 * st] - a[c + 2 * st]) * coe;
+    }
+    return weno5(v1, v2, v3, v4, v5);
+}
+struct OpWeno
+{
+    static __device__ __forceinline__ double apply(const Band& b, double* buf, double* cf, int tl, int PW, ptrdiff_t gidx)
+    {
+        const int c = tl + 3 * PW + 3;  // centre of the 7 x 7 window
+        const double u = b.aux0[gidx], v = b.aux1[gidx];
+        const double Fx = weno_line(buf, c, 1, u, b.p0);
+        const double Fy = weno_line(buf, c, PW, v, b.p1);
+        return u * Fx + v * Fy;
     }
 };
 
@@ -482,11 +537,13 @@ __global__ void __launch_bounds__(NT + 32, MINB) stream_tile_kernel(const __grid
             if (i_lo == 0 && i_hi == SR)
             {
 #pragma unroll
-                for (int i = 0; i < SR; ++i) o[(ptrdiff_t)i * b.nx] = Op::apply(b, buf, cf, tl0 + i * PW, PW);
+                for (int i = 0; i < SR; ++i)
+                    o[(ptrdiff_t)i * b.nx] = Op::apply(b, buf, cf, tl0 + i * PW, PW, (ptrdiff_t)(ybase + i) * b.nx + gx);
             }
             else
             {
-                for (int i = i_lo; i < i_hi; ++i) o[(ptrdiff_t)i * b.nx] = Op::apply(b, buf, cf, tl0 + i * PW, PW);
+                for (int i = i_lo; i < i_hi; ++i)
+                    o[(ptrdiff_t)i * b.nx] = Op::apply(b, buf, cf, tl0 + i * PW, PW, (ptrdiff_t)(ybase + i) * b.nx + gx);
             }
         }
         else if (zr)

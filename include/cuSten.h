@@ -148,6 +148,11 @@ void cuStenCreate2DXYpFun(cuSten_t* pt_cuSten, int deviceNum, int numTiles, int 
                           int numStenVert, int numStenTop, int numStenBottom, double* func);
 CUSTEN_DECL_COMMON(XYpFun)
 
+// ---- XY WENO advection: u dphi/dx + v dphi/dy, periodic, fifth-order upwinded (reference cuSten_struct_functions.h:309) -
+void cuStenCreate2DXYWENOADVp(cuSten_t* pt_cuSten, int deviceNum, int numTiles, int nx, int ny, int BLOCK_X, int BLOCK_Y,
+                              double dx, double dy, double* u, double* v, double* dataOutput, double* dataInput);
+CUSTEN_DECL_COMMON(XYWENOADVp)
+
 #undef CUSTEN_DECL_COMMON
 
 #endif  // CUSTEN_B200_CUSTEN_H

@@ -9,7 +9,7 @@
  *   custenDestroy2D<V>  <->  cuStenDestroy2D<V>   (same header)
  *   custenCompute2D<V>  <->  cuStenCompute2D<V>   cuSten/src/kernels/stencil_kernels.h:52-189
  *   custenCheckError    <->  checkError           cuSten/src/util/util.h:43
- *   <V> in { Xp, Xnp, XpFun, XnpFun, Yp, Ynp, YpFun, YnpFun, XYp, XYnp, XYpFun, XYnpFun }
+ *   <V> in { Xp, Xnp, XpFun, XnpFun, Yp, Ynp, YpFun, YnpFun, XYp, XYnp, XYpFun, XYnpFun, XYWENOADVp }
  *
  * The handle is the reference's cuSten_t (cuSten/src/struct/cuSten_struct_type.h:84-122): caller-allocated,
  * custen_handle_size() bytes, public fields at the reference's offsets.  Error behaviour is the reference's:
@@ -69,6 +69,11 @@ CUSTEN_C_COMMON(XYpFun)
 void custenCreate2DXYnpFun(CUSTEN_C_PREFIX, double* coe, int numStenHoriz, int numStenLeft, int numStenRight,
                            int numStenVert, int numStenTop, int numStenBottom, double* func);
 CUSTEN_C_COMMON(XYnpFun)
+
+/* 13th variant: periodic WENO5 advection (cuStenCreate2DXYWENOADVp, cuSten_struct_functions.h:309) */
+void custenCreate2DXYWENOADVp(cuSten_c_handle* pt_cuSten, int deviceNum, int numTiles, int nx, int ny, int BLOCK_X,
+                              int BLOCK_Y, double dx, double dy, double* u, double* v, double* dataOutput, double* dataInput);
+CUSTEN_C_COMMON(XYWENOADVp)
 
 void custenCheckError(const char* action);
 

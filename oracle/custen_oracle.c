@@ -153,3 +153,54 @@ int custen_oracle_sweep(int dir, int periodic, int fun, const double* in, double
     free(win);
     return rc;
 }
+
+
+/* ---- WENO5 advection (13th variant): u dphi/dx + v dphi/dy, periodic --------------------------------------------
+ * Follows 2d_xyADVWENO_p_kernel.cu:51-86 (wenoSten) and :283-390 (upwinded one-sided differences).  The reference
+ * squares through the single-precision powf; CUDA's powf is not correctly rounded and is not reproducible on a CPU,
+ * so this restatement (libm powf) agrees with the GPU kernels only to single-precision rounding of the smoothness
+ * terms: it is a sanity oracle for the WENO variant (tolerance in tests/test_weno_gpu.py); bit-level parity for that
+ * variant is against the reference's own CUDA kernel. */
+static double weno5_cpu(double v1, double v2, double v3, double v4, double v5)
+{
+    const double epsilon = 1e-06;
+    const double phi1 = (1.0 / 3.0) * v1 - (7.0 / 6.0) * v2 + (11.0 / 6.0) * v3;
+    const double phi2 = -(1.0 / 6.0) * v2 + (5.0 / 6.0) * v3 + (1.0 / 3.0) * v4;
+    const double phi3 = (1.0 / 3.0) * v3 + (5.0 / 6.0) * v4 - (1.0 / 6.0) * v5;
+    const double s1 = (13.0 / 12.0) * powf(v1 - 2.0 * v2 + v3, 2.0) + 0.25 * powf(v1 - 4.0 * v2 + 3.0 * v3, 2.0);
+    const double s2 = (13.0 / 12.0) * powf(v2 - 2.0 * v3 + v4, 2.0) + 0.25 * powf(v2 - v4, 2.0);
+    const double s3 = (13.0 / 12.0) * powf(v3 - 2.0 * v4 + v5, 2.0) + 0.25 * powf(3.0 * v3 - 4.0 * v4 + v5, 2.0);
+    const double a1 = 0.1 / powf(s1 + epsilon, 2.0);
+    const double a2 = 0.6 / powf(s2 + epsilon, 2.0);
+    const double a3 = 0.3 / powf(s3 + epsilon, 2.0);
+    const double denom = 1.0 / (a1 + a2 + a3);
+    return phi1 * (a1 * denom) + phi2 * (a2 * denom) + phi3 * (a3 * denom);
+}
+
+static double weno_line_cpu(const double* in, int nx, int ny, int x, int y, int along_x, double vel, double coe)
+{
+    double a[7];
+    for (int k = -3; k <= 3; ++k)
+    {
+        const int gx = along_x ? wrap(x + k, nx) : x;
+        const int gy = along_x ? y : wrap(y + k, ny);
+        a[k + 3] = in[(size_t)gy * nx + gx];
+    }
+    if (vel > 0.0)
+        return weno5_cpu((a[1] - a[0]) * coe, (a[2] - a[1]) * coe, (a[3] - a[2]) * coe, (a[4] - a[3]) * coe, (a[5] - a[4]) * coe);
+    return weno5_cpu((a[6] - a[5]) * coe, (a[5] - a[4]) * coe, (a[4] - a[3]) * coe, (a[3] - a[2]) * coe, (a[2] - a[1]) * coe);
+}
+
+int custen_oracle_weno(const double* in, const double* u, const double* v, double* out, int nx, int ny, double dx, double dy)
+{
+    const double cx = 1.0 / dx, cy = 1.0 / dy;
+    for (int y = 0; y < ny; ++y)
+        for (int x = 0; x < nx; ++x)
+        {
+            const size_t i = (size_t)y * nx + x;
+            const double fx = weno_line_cpu(in, nx, ny, x, y, 1, u[i], cx);
+            const double fy = weno_line_cpu(in, nx, ny, x, y, 0, v[i], cy);
+            out[i] = u[i] * fx + v[i] * fy;
+        }
+    return 0;
+}

@@ -191,3 +191,63 @@ EXPORT double ref_time(int variant, int nx, int ny, int tiles, int bx, int by, c
     cudaFree(r.coef);
     return ms_per;
 }
+
+
+// 13th variant: the reference's WENO advection kernel on host arrays (managed buffers inside, like its example
+// examples/src/2d_xyWENOADV_p.cu).
+EXPORT int ref_weno(const double* in_host, const double* u_host, const double* v_host, double* out_host, int nx, int ny,
+                    int tiles, int bx, int by, double dx, double dy)
+{
+    const size_t n = (size_t)nx * ny;
+    double *in, *out, *u, *v;
+    cudaMallocManaged(&in, n * sizeof(double));
+    cudaMallocManaged(&out, n * sizeof(double));
+    cudaMallocManaged(&u, n * sizeof(double));
+    cudaMallocManaged(&v, n * sizeof(double));
+    memcpy(in, in_host, n * sizeof(double));
+    memcpy(u, u_host, n * sizeof(double));
+    memcpy(v, v_host, n * sizeof(double));
+    memcpy(out, out_host, n * sizeof(double));
+    cuSten_t h;
+    cuStenCreate2DXYWENOADVp(&h, 0, tiles, nx, ny, bx, by, dx, dy, u, v, out, in);
+    cuStenCompute2DXYWENOADVp(&h, false);
+    cudaDeviceSynchronize();
+    checkError("reference WENO sweep");
+    memcpy(out_host, out, n * sizeof(double));
+    cuStenDestroy2DXYWENOADVp(&h);
+    cudaFree(in); cudaFree(out); cudaFree(u); cudaFree(v);
+    return 0;
+}
+
+EXPORT double ref_weno_time(int nx, int ny, int bx, int by, int warmup, int iters)
+{
+    const size_t n = (size_t)nx * ny;
+    double *in, *out, *u, *v;
+    cudaMallocManaged(&in, n * sizeof(double));
+    cudaMallocManaged(&out, n * sizeof(double));
+    cudaMallocManaged(&u, n * sizeof(double));
+    cudaMallocManaged(&v, n * sizeof(double));
+    for (double* p : {in, out, u, v}) cudaMemPrefetchAsync(p, n * sizeof(double), 0, 0);
+    ref_fill<<<1024, 256>>>(in, n, 1);
+    ref_fill<<<1024, 256>>>(u, n, 2);
+    ref_fill<<<1024, 256>>>(v, n, 3);
+    cudaMemset(out, 0, n * sizeof(double));
+    cudaDeviceSynchronize();
+    cuSten_t h;
+    cuStenCreate2DXYWENOADVp(&h, 0, 1, nx, ny, bx, by, 1.0 / nx, 1.0 / ny, u, v, out, in);
+    for (int i = 0; i < warmup; ++i) cuStenCompute2DXYWENOADVp(&h, false);
+    cudaDeviceSynchronize();
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, 0);
+    for (int i = 0; i < iters; ++i) cuStenCompute2DXYWENOADVp(&h, false);
+    cudaEventRecord(e1, 0);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    checkError("reference WENO timing");
+    cuStenDestroy2DXYWENOADVp(&h);
+    cudaFree(in); cudaFree(out); cudaFree(u); cudaFree(v);
+    return ms / iters;
+}

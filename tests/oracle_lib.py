@@ -126,6 +126,31 @@ def ref_time(variant, nx, ny, coef, H=1, L=0, R=0, V=1, T=0, B=0, fun=None, tile
                         H, L, R, V, T, B, fun.encode() if fun else None, warmup, iters)
 
 
+def oracle_weno(inp, u, v, dx, dy):
+    lib = oracle()
+    lib.custen_oracle_weno.argtypes = [_dp] * 4 + [ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double]
+    lib.custen_oracle_weno.restype = ctypes.c_int
+    inp, u, v = (np.ascontiguousarray(a, dtype=np.float64) for a in (inp, u, v))
+    out = np.zeros_like(inp)
+    ny, nx = inp.shape
+    lib.custen_oracle_weno(inp.ctypes.data_as(_dp), u.ctypes.data_as(_dp), v.ctypes.data_as(_dp), out.ctypes.data_as(_dp),
+                           nx, ny, dx, dy)
+    return out
+
+
+def ref_weno(inp, u, v, dx, dy, tiles=1, block=(32, 32), out_init=None):
+    """The reference's WENO kernel (sm_100 rebuild)."""
+    lib = ref_gpu()
+    lib.ref_weno.argtypes = [_dp] * 4 + [ctypes.c_int] * 5 + [ctypes.c_double, ctypes.c_double]
+    lib.ref_weno.restype = ctypes.c_int
+    inp, u, v = (np.ascontiguousarray(a, dtype=np.float64) for a in (inp, u, v))
+    out = np.zeros_like(inp) if out_init is None else out_init.copy()
+    ny, nx = inp.shape
+    lib.ref_weno(inp.ctypes.data_as(_dp), u.ctypes.data_as(_dp), v.ctypes.data_as(_dp), out.ctypes.data_as(_dp), nx, ny,
+                 tiles, block[0], block[1], dx, dy)
+    return out
+
+
 _cahn_ref = None
 
 

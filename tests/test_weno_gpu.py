@@ -1,0 +1,102 @@
+"""13th public variant, cuStenCreate/Compute/Swap/Destroy2DXYWENOADVp: periodic fifth-order WENO advection.
+Bit-level parity is against the reference's own CUDA kernel (it squares through single-precision powf, which no CPU
+libm reproduces); the CPU oracle is a sanity check at single-precision tolerance."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+import custen_b200 as cs  # noqa: E402
+
+
+def _fields(nx, ny, seed=0):
+    x = np.arange(nx) * (2 * np.pi / nx)
+    y = np.arange(ny) * (2 * np.pi / ny)
+    rng = np.random.default_rng(seed)
+    phi = np.sin(x)[None, :] * np.cos(y)[:, None] + 0.05 * rng.uniform(-1, 1, (ny, nx))
+    u = np.cos(y)[:, None] * np.ones((1, nx)) + 0.1 * rng.uniform(-1, 1, (ny, nx))   # both signs
+    v = -np.sin(x)[None, :] * np.ones((ny, 1)) + 0.1 * rng.uniform(-1, 1, (ny, nx))
+    return phi, u, v
+
+
+def _ours(phi, u, v, dx, dy, tiles=1, kind="device", fallback=False):
+    ny, nx = phi.shape
+    cs.set_tuning(force_fallback=1 if fallback else 0)
+    h = cs.cuSten_t()
+    if kind == "device":
+        t = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (phi, u, v)]
+        out = torch.zeros_like(t[0])
+        cs.cuStenCreate2DXYWENOADVp(h, 0, tiles, nx, ny, 32, 16, dx, dy, t[1], t[2], out, t[0])
+        cs.cuStenCompute2DXYWENOADVp(h, cs.DEVICE)
+        cs.device_synchronize()
+        res = out.cpu().numpy()
+    else:
+        import ctypes
+        lib = cs.load()
+        n = nx * ny
+        ptrs = [lib.custen_managed_alloc(n * 8) for _ in range(4)]
+        views = [np.ctypeslib.as_array((ctypes.c_double * n).from_address(p)) for p in ptrs]
+        for vw, a in zip(views[:3], (phi, u, v)):
+            vw[:] = a.ravel()
+        views[3][:] = 0.0
+        cs.cuStenCreate2DXYWENOADVp(h, 0, tiles, nx, ny, 32, 16, dx, dy, ptrs[1], ptrs[2], ptrs[3], ptrs[0])
+        cs.cuStenCompute2DXYWENOADVp(h, cs.HOST)
+        cs.device_synchronize()
+        res = views[3].reshape(ny, nx).copy()
+    path = cs.last_path(h)
+    cs.cuStenDestroy2DXYWENOADVp(h)
+    if kind != "device":
+        for p in ptrs:
+            lib.custen_managed_free(p)
+    cs.set_tuning()
+    return res, path
+
+
+@pytest.mark.parametrize("nx,ny,tiles", [(256, 128, 1), (512, 512, 4), (1024, 256, 2)])
+def test_bit_exact_against_reference_weno_kernel(nx, ny, tiles):
+    phi, u, v = _fields(nx, ny, seed=nx)
+    dx, dy = 2 * np.pi / nx, 2 * np.pi / ny
+    ref = ol.ref_weno(phi, u, v, dx, dy, tiles=tiles, block=(32, 16))
+    got, path = _ours(phi, u, v, dx, dy, tiles=tiles)
+    assert path == "stream_tile"
+    assert ol.count_diff(got, ref) == 0
+    got_fb, path = _ours(phi, u, v, dx, dy, tiles=tiles, fallback=True)
+    assert path == "fallback" and ol.count_diff(got_fb, ref) == 0
+    got_m, _ = _ours(phi, u, v, dx, dy, tiles=tiles, kind="managed")
+    assert ol.count_diff(got_m, ref) == 0
+
+
+def test_cpu_oracle_agrees_to_single_precision():
+    nx, ny = 128, 96
+    phi, u, v = _fields(nx, ny, seed=5)
+    dx, dy = 2 * np.pi / nx, 2 * np.pi / ny
+    got, _ = _ours(phi, u, v, dx, dy)
+    want = ol.oracle_weno(phi, u, v, dx, dy)
+    assert np.max(np.abs(got - want)) / np.max(np.abs(want)) < 1e-5
+    # and it approximates u dphi/dx + v dphi/dy of the smooth part
+    assert np.isfinite(got).all()
+
+
+def test_swap_time_stepping():
+    nx, ny = 256, 128
+    phi, u, v = _fields(nx, ny, seed=9)
+    dx, dy = 2 * np.pi / nx, 2 * np.pi / ny
+    t = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (phi, u, v)]
+    out = torch.zeros_like(t[0])
+    h = cs.cuSten_t()
+    cs.cuStenCreate2DXYWENOADVp(h, 0, 2, nx, ny, 32, 16, dx, dy, t[1], t[2], out, t[0])
+    cs.cuStenCompute2DXYWENOADVp(h, cs.DEVICE)
+    cs.device_synchronize()
+    cs.cuStenSwap2DXYWENOADVp(h, out)
+    cs.cuStenCompute2DXYWENOADVp(h, cs.DEVICE)   # now t[0] <- weno(out)
+    cs.device_synchronize()
+    step1 = ol.ref_weno(phi, u, v, dx, dy, tiles=2, block=(32, 16))
+    step2 = ol.ref_weno(step1, u, v, dx, dy, tiles=2, block=(32, 16))
+    assert ol.count_diff(out.cpu().numpy(), step1) == 0
+    assert ol.count_diff(t[0].cpu().numpy(), step2) == 0
+    cs.cuStenDestroy2DXYWENOADVp(h)
