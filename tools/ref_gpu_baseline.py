@@ -34,6 +34,14 @@ def main(out, n):
     ms = ol.ref_time("XYpFun", n, n, coef, tiles=1, block=(8, 8), warmup=3, iters=10, **kw)
     res["rows"]["XYpFun_8x8"] = {"block": (8, 8), "ms": ms, "gpoints_per_s": n * n / ms / 1e6}
     print("XYpFun_8x8", res["rows"]["XYpFun_8x8"], flush=True)
+    # 13th variant: WENO advection (32x32 blocks as examples/src/2d_xyWENOADV_p.cu:38-39; 32x16 if that cannot launch)
+    lib = ol.ref_gpu()
+    import ctypes
+    lib.ref_weno_time.argtypes = [ctypes.c_int] * 6
+    lib.ref_weno_time.restype = ctypes.c_double
+    ms = lib.ref_weno_time(n, n, 32, 16, 3, 10)
+    res["rows"]["XYWENOADVp"] = {"block": (32, 16), "ms": ms, "gpoints_per_s": n * n / ms / 1e6}
+    print("XYWENOADVp", res["rows"]["XYWENOADVp"], flush=True)
     # config 5: the reference's GPU Cahn-Hilliard solver, ms per step
     for ncahn, steps in ((512, 20), (4096, 5)):
         c0 = np.random.default_rng(0).uniform(-0.1, 0.1, (ncahn, ncahn))
