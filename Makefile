@@ -15,8 +15,8 @@ CORE_OBJ  := $(patsubst %.cu,$(OBJDIR)/%.o,$(CORE_SRC))
 CABI_OBJ  := $(patsubst %.cu,$(OBJDIR)/%.o,$(CABI_SRC))
 HEADERS   := $(wildcard $(SRCDIR)/*.h $(SRCDIR)/*.cuh include/*.h)
 
-.PHONY: all lib oracle clean
-all: lib oracle
+.PHONY: all lib oracle examples clean
+all: lib oracle examples
 
 lib: $(LIBDIR)/libcuSten.a $(LIBDIR)/libcusten_b200.so
 
@@ -32,8 +32,15 @@ $(LIBDIR)/libcusten_b200.so: $(CORE_OBJ) $(CABI_OBJ)
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(ARCH) -shared -o $@ $(CORE_OBJ) $(CABI_OBJ)
 
+# the re-hosted Cahn-Hilliard driver program (reference: cuPentSpeedUp/cuPentCahnADITiming)
+examples: examples/bin/cuPentCahnADI
+
+examples/bin/cuPentCahnADI: examples/cuPentCahnADI.cu $(LIBDIR)/libcusten_b200.so
+	@mkdir -p examples/bin
+	$(NVCC) $(ARCH) -O3 -std=c++17 -o $@ $< -L$(LIBDIR) -lcusten_b200 -Xlinker -rpath -Xlinker '$$ORIGIN/../../$(LIBDIR)'
+
 oracle:
 	$(MAKE) -C oracle
 
 clean:
-	rm -rf build $(LIBDIR) oracle/_ref
+	rm -rf build $(LIBDIR) oracle/_ref examples/bin

@@ -466,7 +466,7 @@ def main():
     ap.add_argument("--transport", default="peer", choices=["exchange", "peer"],
                     help="halo transport at N > 1: 'peer' reads the neighbours' edge rows in place over NVLink (IPC), "
                          "'exchange' sends them with NCCL every step")
-    ap.add_argument("--e2e-tiles", type=int, default=8)
+    ap.add_argument("--e2e-tiles", type=int, default=32)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-table", action="store_true")

@@ -76,3 +76,18 @@ def test_steps_compose():
     b = s.field()
     s.destroy()
     assert ol.count_diff(a, b) == 0
+
+
+def test_rehosted_driver_program_runs():
+    """examples/cuPentCahnADI.cu: the reference timing twin's command line on the new engine."""
+    import os
+    import re
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "bin", "cuPentCahnADI")
+    if not os.path.exists(exe):
+        pytest.skip("examples not built (make examples)")
+    r = subprocess.run([exe, "256", "40"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert float(r.stdout.split()[0]) > 0.0
+    m = re.search(r"mean\(c\) = (\S+), max\|c\| = (\S+)", r.stderr)
+    assert m and abs(float(m.group(1))) < 1e-3 and 0.0 < float(m.group(2)) < 1.5
