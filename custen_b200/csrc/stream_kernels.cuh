@@ -103,7 +103,7 @@ struct StageDesc
 {
     int x0;      // first column of the strip
     int row0;    // band-local input row held by stage row 0
-    int nrows;   // valid rows in this stage; < 0 terminates the consumers
+    int nrows;   // valid rows in this stage
     int out_lo;  // output rows this work item may write: [out_lo, out_hi)
     int out_hi;
     int first;   // 1: first stage of a work item (register accumulators restart)
@@ -115,6 +115,22 @@ constexpr int SMEM_DESC_OFF = 128;    // NS descriptors of 32 B
 constexpr int SMEM_COEF_OFF = 512;    // up to 128 coefficients
 constexpr int SMEM_STAGE_OFF = 1536;  // stage ring
 constexpr int MAX_SMEM_COEF = 128;
+
+// Stages the producer will emit for this CTA (static round-robin over work items): the consumers count the same
+// number, so the ring needs no termination message.
+template <int SR>
+__device__ __forceinline__ int cta_stage_count(const StreamArgs& a)
+{
+    int total = 0;
+    for (int item = blockIdx.x; item < a.nitems; item += gridDim.x)
+    {
+        const int chunk = item / a.nstrips;
+        const int out_lo = chunk * a.chunk_rows;
+        const int out_hi = min(out_lo + a.chunk_rows, a.b.rows);
+        total += (out_hi - out_lo + a.b.T + a.Beff + SR - 1) / SR;
+    }
+    return total;
+}
 
 // Producer: one warp.  Lane l owns stage row l: it works out where that grid row lives (band, top strip,
 // bottom strip; wrapped columns) and issues up to three bulk copies for it.
@@ -185,15 +201,6 @@ __device__ __forceinline__ void producer_loop(const StreamArgs& a, unsigned char
             }
             if (++s == NS) { s = 0; ph ^= 1; }
         }
-    }
-    // terminate the consumers
-    mbar_wait(empty0 + 8 * s, ph ^ 1);
-    if (lane == 0)
-    {
-        StageDesc d;
-        d.x0 = 0; d.row0 = 0; d.nrows = -1; d.out_lo = 0; d.out_hi = 0; d.first = 0;
-        desc[s] = d;
-        mbar_arrive(full0 + 8 * s);
     }
 }
 
@@ -282,11 +289,11 @@ __global__ void __launch_bounds__(NT + 32, MINB) stream_acc_kernel(const __grid_
 
     int s = 0;
     uint32_t ph = 0;
-    for (;;)
+    const int nstages = cta_stage_count<SR>(a);
+    for (int sc = 0; sc < nstages; ++sc)
     {
         mbar_wait(full0 + 8 * s, ph);
         const StageDesc d = desc[s];
-        if (d.nrows < 0) break;
         const double* buf = stage0 + (size_t)s * a.stage_doubles;
         const int gx = d.x0 + CPT * t;
         const ColMask cm = make_colmask(b, gx);
@@ -516,11 +523,11 @@ __global__ void __launch_bounds__(NT + 32, MINB) stream_tile_kernel(const __grid
 
     int s = 0;
     uint32_t ph = 0;
-    for (;;)
+    const int nstages = cta_stage_count<SR>(a);
+    for (int sc = 0; sc < nstages; ++sc)
     {
         mbar_wait(full0 + 8 * s, ph);
         const StageDesc d = desc[s];
-        if (d.nrows < 0) break;
         double* buf = stage0 + (size_t)s * a.stage_doubles;
 
         const int gx = d.x0 + t;
