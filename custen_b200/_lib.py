@@ -39,7 +39,7 @@ EXPORTED = (
        "custen_event_synchronize", "custen_event_elapsed_ms", "custen_event_destroy", "custen_host_alloc",
        "custen_host_free", "custen_managed_alloc", "custen_managed_free", "custen_peer_barrier", "custen_device_alloc",
        "custen_device_free", "custen_cahn_create", "custen_cahn_set_field", "custen_cahn_step", "custen_cahn_get_field",
-       "custen_cahn_time_steps", "custen_cahn_destroy"]
+       "custen_cahn_time_steps", "custen_cahn_destroy", "custen_debug_bands"]
 )
 
 _lib = None
@@ -99,7 +99,26 @@ def load():
     lib.custen_cahn_get_field.argtypes, lib.custen_cahn_get_field.restype = [_c_void_p, _c_void_p], None
     lib.custen_cahn_time_steps.argtypes, lib.custen_cahn_time_steps.restype = [_c_void_p, _c_int], ctypes.c_float
     lib.custen_cahn_destroy.argtypes, lib.custen_cahn_destroy.restype = [_c_void_p], None
+    lib.custen_debug_bands.argtypes = [_c_int] * 14 + [_c_void_p, _c_int]
+    lib.custen_debug_bands.restype = _c_int
     lib.custen_managed_alloc.argtypes, lib.custen_managed_alloc.restype = [ctypes.c_size_t], ctypes.c_void_p
     lib.custen_managed_free.argtypes, lib.custen_managed_free.restype = [_c_void_p], None
     _lib = lib
     return lib
+
+
+class BandDesc(ctypes.Structure):
+    """Record written by custen_debug_bands (custen_b200/csrc/plan.h BandDesc)."""
+    _fields_ = ([(n, ctypes.c_longlong) for n in ("in_off", "out_off", "top_off", "bottom_off")]
+                + [(n, ctypes.c_int) for n in ("top_kind", "bottom_kind", "rows", "nx", "L", "R", "T", "B", "H", "V", "wrap_x",
+                                               "xlo", "xhi", "ylo", "yhi", "zero_right", "contiguous")])
+
+
+def debug_bands(variant, numTiles, nx, ny, H=1, L=0, R=0, V=1, T=0, B=0, merged=False, slab=None):
+    """Bands Compute would launch (no CUDA).  slab = None or (is_first, is_last)."""
+    lib = load()
+    arr = (BandDesc * 64)()
+    n = lib.custen_debug_bands(VARIANTS.index(variant), numTiles, nx, ny, H, L, R, V, T, B, int(merged),
+                               0 if slab is None else 1, 0 if slab is None else int(slab[0]),
+                               0 if slab is None else int(slab[1]), ctypes.addressof(arr), 64)
+    return [arr[i] for i in range(n)]

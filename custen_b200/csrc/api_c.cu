@@ -217,6 +217,13 @@ void* custen_device_alloc(size_t bytes)
 }
 void custen_device_free(void* p) { cudaFree(p); }
 
+int custen_debug_bands(int variant, int numTiles, int nx, int ny, int H, int L, int R, int V, int T, int B, int merged,
+                       int slab, int slab_first, int slab_last, void* out, int max_out)
+{
+    return debug_bands(variant, numTiles, nx, ny, H, L, R, V, T, B, merged, slab, slab_first, slab_last,
+                       reinterpret_cast<BandDesc*>(out), max_out);
+}
+
 void* custen_event_create(void)
 {
     cudaEvent_t e;

@@ -53,9 +53,11 @@ static void set_boundaries(cuSten_t* h, double* base)
     }
 }
 
+// `dry` builds the plan without touching CUDA (no device, streams or events): used by custen_debug_bands so that
+// the tiling / seam / mask logic can be tested on a machine without a GPU.
 static void plan_create_impl(cuSten_t* h, Spec spec, int nstreams, int deviceNum, int numTiles, int nx, int ny, int BLOCK_X,
                              int BLOCK_Y, double* dataOutput, double* dataInput, double* coef, int H, int L, int R, int V,
-                             int T, int B, int numCoe, double* func)
+                             int T, int B, int numCoe, double* func, bool dry = false)
 {
     memset(h, 0, sizeof *h);
     h->deviceNum = deviceNum;
@@ -66,18 +68,21 @@ static void plan_create_impl(cuSten_t* h, Spec spec, int nstreams, int deviceNum
     h->BLOCK_X = BLOCK_X;
     h->BLOCK_Y = BLOCK_Y;
 
-    cudaSetDevice(deviceNum);
-    check("Setting current device", deviceNum);
+    if (!dry)
+    {
+        cudaSetDevice(deviceNum);
+        check("Setting current device", deviceNum);
+    }
 
     // the public streams (blocking, like the reference's cudaStreamCreate; 3, or 6 for WENO) + hidden tail
     h->streams = (cudaStream_t*)calloc(nstreams + 2, sizeof(cudaStream_t));
-    for (int s = 0; s < nstreams; ++s)
+    for (int s = 0; s < nstreams && !dry; ++s)
     {
         cudaStreamCreate(&h->streams[s]);
         check("Creating stream", deviceNum);
     }
     h->events = (cudaEvent_t*)calloc(2, sizeof(cudaEvent_t));
-    for (int e = 0; e < 2; ++e)
+    for (int e = 0; e < 2 && !dry; ++e)
     {
         cudaEventCreateWithFlags(&h->events[e], cudaEventDisableTiming);
         check("Creating event", deviceNum);
@@ -541,6 +546,61 @@ void plan_compute(cuSten_t* h, bool offload)
     if (kin == MK_HOST || kout == MK_HOST) compute_staged(h, p, coef);
     else if (kin == MK_MANAGED || kout == MK_MANAGED) compute_managed(h, p, coef, kcoef, offload);
     else compute_resident(h, p, coef);
+}
+
+// ---- host-logic probe (no CUDA) --------------------------------------------------------------------------------
+// Builds the plan of a variant on fake base addresses and reports the bands Compute would launch: per tile
+// (merged == 0) or as one band over all tiles (merged == 1).  Offsets are in doubles from the input / output base.
+int debug_bands(int variant, int numTiles, int nx, int ny, int H, int L, int R, int V, int T, int B, int merged,
+                int slab, int slab_first, int slab_last, BandDesc* out, int max_out)
+{
+    static const Spec specs[12] = {{DIR_X, 1, 0, 0}, {DIR_X, 0, 0, 0}, {DIR_X, 1, 1, 0}, {DIR_X, 0, 1, 0},
+                                   {DIR_Y, 1, 0, 0}, {DIR_Y, 0, 0, 0}, {DIR_Y, 1, 1, 0}, {DIR_Y, 0, 1, 0},
+                                   {DIR_XY, 1, 0, 0}, {DIR_XY, 0, 0, 0}, {DIR_XY, 1, 1, 0}, {DIR_XY, 0, 1, 0}};
+    if (variant < 0 || variant >= 12) return -1;
+    const Spec sp = specs[variant];
+    double* const in = reinterpret_cast<double*>((uintptr_t)1 << 40);
+    double* const outp = reinterpret_cast<double*>((uintptr_t)1 << 41);
+    double* const top_halo = reinterpret_cast<double*>((uintptr_t)1 << 42);
+    double* const bot_halo = reinterpret_cast<double*>((uintptr_t)1 << 43);
+    cuSten_t h;
+    const int HH = sp.dir == DIR_Y ? 1 : H, VV = sp.dir == DIR_X ? 1 : V;
+    plan_create_impl(&h, sp, 3, 0, numTiles, nx, ny, 32, 8, outp, in, nullptr, HH, sp.dir == DIR_Y ? 0 : L,
+                     sp.dir == DIR_Y ? 0 : R, VV, sp.dir == DIR_X ? 0 : T, sp.dir == DIR_X ? 0 : B, HH * VV, nullptr, true);
+    Plan* p = plan_of(&h);
+    if (slab)
+    {
+        p->slab_enabled = 1;
+        p->slab_top = top_halo;
+        p->slab_bottom = bot_halo;
+        p->slab_first = slab_first;
+        p->slab_last = slab_last;
+    }
+    int n = 0;
+    auto emit = [&](const Band& b) {
+        if (n >= max_out) return;
+        BandDesc& d = out[n++];
+        d.in_off = b.in - in;
+        d.out_off = b.out - outp;
+        d.top_kind = !b.have_top ? 0 : (b.top == top_halo ? 2 : 1);
+        d.top_off = d.top_kind == 1 ? b.top - in : 0;
+        d.bottom_kind = !b.have_bottom ? 0 : (b.bottom == bot_halo ? 2 : 1);
+        d.bottom_off = d.bottom_kind == 1 ? b.bottom - in : 0;
+        d.rows = b.rows; d.nx = b.nx; d.L = b.L; d.R = b.R; d.T = b.T; d.B = b.B; d.H = b.H; d.V = b.V;
+        d.wrap_x = b.wrap_x; d.xlo = b.xlo; d.xhi = b.xhi; d.ylo = b.ylo; d.yhi = b.yhi; d.zero_right = b.zero_right;
+        d.contiguous = tiles_contiguous(&h) ? 1 : 0;
+    };
+    if (merged) emit(make_band(&h, p, nullptr, 0, h.numTiles - 1));
+    else
+        for (int t = 0; t < h.numTiles; ++t) emit(make_band(&h, p, nullptr, t, t));
+    free(p);
+    free(h.streams);
+    free(h.events);
+    free(h.dataInput);
+    free(h.dataOutput);
+    free(h.boundaryTop);
+    free(h.boundaryBottom);
+    return n;
 }
 
 }  // namespace custen

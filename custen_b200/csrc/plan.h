@@ -59,6 +59,17 @@ void plan_compute(cuSten_t* h, bool offload);
 
 MemKind classify(const void* p);
 
+// What one launch would cover, for tests of the host logic (see debug_bands in plan.cu).
+struct BandDesc
+{
+    long long in_off, out_off, top_off, bottom_off;  // in doubles, relative to the input / output base
+    int top_kind, bottom_kind;                       // 0 absent, 1 inside the input array, 2 slab halo buffer
+    int rows, nx, L, R, T, B, H, V;
+    int wrap_x, xlo, xhi, ylo, yhi, zero_right, contiguous;
+};
+int debug_bands(int variant, int numTiles, int nx, int ny, int H, int L, int R, int V, int T, int B, int merged,
+                int slab, int slab_first, int slab_last, BandDesc* out, int max_out);
+
 }  // namespace custen
 
 #endif

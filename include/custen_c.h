@@ -114,6 +114,13 @@ void custen_peer_barrier(cuSten_c_handle* pt_cuSten, void* up_flags, void* down_
 void* custen_device_alloc(size_t bytes);
 void custen_device_free(void* p);
 
+/* Host-logic probe, no CUDA calls: the bands (tile, seam pointers, write masks) Compute would launch for a variant
+ * (index into Xp Xnp XpFun XnpFun Yp Ynp YpFun YnpFun XYp XYnp XYpFun XYnpFun).  `out` receives up to max_out
+ * records of { long long in_off, out_off, top_off, bottom_off; int top_kind, bottom_kind, rows, nx, L, R, T, B, H, V,
+ * wrap_x, xlo, xhi, ylo, yhi, zero_right, contiguous; }; returns the number written. */
+int custen_debug_bands(int variant, int numTiles, int nx, int ny, int H, int L, int R, int V, int T, int B, int merged,
+                       int slab, int slab_first, int slab_last, void* out, int max_out);
+
 /* Event timing on the stream a handle launches on (streams[idx] of the handle). */
 void* custen_event_create(void);
 void custen_event_record(void* ev, cuSten_c_handle* pt_cuSten, int stream_idx);
