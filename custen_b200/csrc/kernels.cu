@@ -151,7 +151,7 @@ template <> struct AccGeom<1, 3> { static constexpr int NT = 256, CPT = 1, SR = 
 template <> struct AccGeom<1, 5> { static constexpr int NT = 512, CPT = 1, SR = 10, NS = 3, MAXCPS = 1; };
 template <> struct AccGeom<1, 7> { static constexpr int NT = 512, CPT = 1, SR = 7, NS = 3, MAXCPS = 1; };
 template <> struct AccGeom<1, 9> { static constexpr int NT = 512, CPT = 1, SR = 9, NS = 3, MAXCPS = 1; };
-template <> struct AccGeom<5, 5> { static constexpr int NT = 512, CPT = 1, SR = 8, NS = 3, MAXCPS = 1; };
+template <> struct AccGeom<5, 5> { static constexpr int NT = 128, CPT = 2, SR = 8, NS = 3, MAXCPS = 2; };
 
 // Work decomposition: column strips x row chunks, chunk height chosen so that the item count is (just under)
 // a whole number of waves of resident CTAs.

@@ -190,14 +190,34 @@ int main(int argc, char** argv)
     fill<<<2048, 256>>>(g_in, n);
     fill<<<1, 128>>>(g_coef, 128);
     cudaDeviceSynchronize();
-    printf("== XY 3x3\n"); sweep<3, 3, 1, 6, 9>();
-    printf("== XY 5x5\n"); sweep<5, 5, 0, 5, 10>();
-    printf("== Y 9\n"); sweep<1, 9, 0, 9, 18>();
-    printf("== Y 3\n"); sweep<1, 3, 0, 6, 9>();
-    printf("== X 9\n"); sweep<9, 1, 0, 4, 16>();
-    printf("== TILE\n");
-    sweep_tile<OpInlineXY<cubic_xy, 3, 3>>("cubic3x3", 3, 3);
-    sweep_tile<OpInlineY<weighted9_y, 4>>("w9y", 1, 9);
+    printf("== XY 5x5\n");
+    for (int rep = 0; rep < 2; ++rep)
+    for (int cps = 1; cps <= 2; ++cps)
+    {
+        run<512, 8, 3, 5, 5, 0, 1>(cps, 192);
+        run<512, 4, 4, 5, 5, 0, 1>(cps, 192);
+        run<512, 4, 6, 5, 5, 0, 1>(cps, 192);
+        run<768, 8, 3, 5, 5, 0, 1>(cps, 192);
+        run<768, 4, 4, 5, 5, 0, 1>(cps, 192);
+        run<992, 8, 3, 5, 5, 0, 1>(cps, 192);
+        run<992, 4, 4, 5, 5, 0, 1>(cps, 192);
+        run<992, 4, 6, 5, 5, 0, 1>(cps, 192);
+        run<384, 8, 3, 5, 5, 0, 1>(cps, 192);
+        run<384, 8, 4, 5, 5, 0, 1>(cps, 192);
+        run<256, 8, 3, 5, 5, 0, 2>(cps, 192);
+        run<384, 8, 3, 5, 5, 0, 2>(cps, 192);
+        run<512, 4, 4, 5, 5, 0, 2>(cps, 192);
+        run<128, 8, 3, 5, 5, 0, 2>(cps, 192);
+        run<128, 8, 4, 5, 5, 0, 2>(cps, 192);
+        run<192, 8, 3, 5, 5, 0, 2>(cps, 192);
+    }
+    for (int cps = 3; cps <= 4; ++cps)
+    {
+        run<128, 8, 3, 5, 5, 0, 2>(cps, 192);
+        run<128, 4, 4, 5, 5, 0, 2>(cps, 192);
+        run<192, 8, 3, 5, 5, 0, 2>(cps, 192);
+        run<256, 8, 3, 5, 5, 0, 1>(cps, 192);
+    }
     std::sort(results.begin(), results.end(), [](const Res& x, const Res& y) { return x.gpts > y.gpts; });
     printf("\n== top 25\n");
     for (size_t i = 0; i < results.size() && i < 25; ++i) printf("%-70s %8.1f\n", results[i].name, results[i].gpts);
