@@ -202,8 +202,10 @@ void custen_peer_barrier(cuSten_c_handle* h, void* up_flags, void* down_flags, v
     unsigned long long* mine = (unsigned long long*)my_flags;
     unsigned long long* up = (unsigned long long*)up_flags;
     unsigned long long* down = (unsigned long long*)down_flags;
-    custen_peer_barrier_kernel<<<1, 1, 0, H(h)->streams[0]>>>(up ? up + 1 : nullptr, down ? down + 0 : nullptr, mine + 0,
-                                                              mine + 1, (unsigned long long)epoch);
+    // no handle: the legacy default stream, which every blocking stream of every handle orders against
+    cudaStream_t st = h ? H(h)->streams[0] : (cudaStream_t)0;
+    custen_peer_barrier_kernel<<<1, 1, 0, st>>>(up ? up + 1 : nullptr, down ? down + 0 : nullptr, mine + 0, mine + 1,
+                                                (unsigned long long)epoch);
     checkError("custen_peer_barrier");
 }
 

@@ -109,7 +109,8 @@ void custen_ipc_close(void* mapped_ptr);
 
 /* Neighbour barrier for the "peer" halo transport: flag words live in custen_device_alloc'ed memory (2 x u64 per
  * rank, zero-initialised, exported with custen_ipc_export); up_flags / down_flags are the neighbours' mapped flag
- * blocks (NULL where there is no neighbour).  Enqueued on the handle's compute stream. */
+ * blocks (NULL where there is no neighbour).  Enqueued on the handle's compute stream, or on the legacy default
+ * stream when pt_cuSten is NULL. */
 void custen_peer_barrier(cuSten_c_handle* pt_cuSten, void* up_flags, void* down_flags, void* my_flags, uint64_t epoch);
 void* custen_device_alloc(size_t bytes);
 void custen_device_free(void* p);
@@ -145,6 +146,23 @@ void custen_cahn_step(void* solver, int nsteps);               /* asynchronous *
 void custen_cahn_get_field(void* solver, double* out_host);     /* synchronises */
 float custen_cahn_time_steps(void* solver, int nsteps);         /* milliseconds for nsteps steps (CUDA events) */
 void custen_cahn_destroy(void* solver);
+
+/* The same solver on one y-slab of the grid (one process per GPU; BASELINE.json config 5 at 2-8 GPUs), driven phase by
+ * phase so that the caller can place the neighbour barrier and the two all-to-all transposes between the phases
+ * (custen_b200/cahn.py CahnHilliardSlab does this over torch.distributed / NCCL):
+ *   phase 0: cBar = 2c - cOld          -> neighbour barrier (halo rows of c and cBar are read from peer memory)
+ *   phase 1: both stencils, right-hand side, x-direction solve -> all-to-all of buffer 3 into buffer 4
+ *   phase 2: gather whole columns, y-direction solve           -> all-to-all of buffer 5 into buffer 4
+ *   phase 3: c(t + dt) = cBar + w, field buffers trade roles
+ * buffers: 0 / 1 the two field buffers, 2 cBar, 3 x-solve result (n x rows), 4 receive buffer, 5 y-solve result (n x cols);
+ * handles: 0 / 1 nonlinear term on field buffer 0 / 1, 2 linear term on cBar (for custen_set_slab). */
+void* custen_cahn_slab_create(int nx, int rank, int world, double D, double gamma, double lx, double dt_over_dx, int device);
+void* custen_cahn_slab_buffer(void* solver, int which);
+void* custen_cahn_slab_handle(void* solver, int which);
+int custen_cahn_slab_current(void* solver);
+void custen_cahn_slab_phase(void* solver, int phase);
+void custen_cahn_slab_set_field(void* solver, const double* rows_host);
+void custen_cahn_slab_get_field(void* solver, double* rows_host);
 
 #ifdef __cplusplus
 }
