@@ -294,7 +294,35 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
         path = ss.st.path
+        # halo traffic: (T + B) rows of nx doubles per GPU per sweep; timed on its own as an NCCL exchange
+        T, B = kw.get("T", 0), kw.get("B", 0)
+        halo = None
+        if T + B:
+            periodic = not variant.replace("Fun", "").endswith("np")
+            top = torch.empty((max(T, 1), n), device="cuda", dtype=torch.float64)
+            bot = torch.empty((max(B, 1), n), device="cuda", dtype=torch.float64)
+            for _ in range(3):
+                slab.exchange_halos(inp, T, B, top[:T], bot[:B], rank, world, periodic)
+            torch.cuda.synchronize()
+            dist.barrier()
+            h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            h0.record()
+            for _ in range(20):
+                slab.exchange_halos(inp, T, B, top[:T], bot[:B], rank, world, periodic)
+            h1.record()
+            torch.cuda.synchronize()
+            th = torch.tensor([h0.elapsed_time(h1) / 20], device="cuda", dtype=torch.float64)
+            dist.all_reduce(th, op=dist.ReduceOp.MAX)
+            hb = (T + B) * n * 8
+            halo = {"bytes_received_per_gpu_per_sweep": hb, "transport_in_timed_region": args.transport,
+                    "nccl_exchange_us": round(float(th.item()) * 1e3, 1),
+                    "nccl_exchange_nvlink_gbs_per_gpu": round(hb / (float(th.item()) * 1e-3) / 1e9, 2),
+                    "in_sweep_gbs_per_gpu": round(hb / (ms / args.steps * 1e-3) / 1e9, 2),
+                    "note": "peer transport: the sweep's TMA producer reads the rows from the neighbours' memory, no separate "
+                            "exchange; the NCCL figure is the same rows sent with send/recv on their own (latency-bound)"}
         ss.destroy()
+    if world == 1:
+        halo = None
     clocks = sampler.stop()
     ms_per_step = ms / args.steps
     value = n * n / ms_per_step / 1e6  # Gpoints/s, whole job
@@ -450,6 +478,8 @@ def run_ours(args, rank, world, local_rank):
                              "launching stream over the timed region); per GPU"},
         "cpu_baseline": cpu,
     }
+    if halo:
+        line["halo_exchange"] = halo
     line.update(extras)
     print(json.dumps(line))
     if dist:
