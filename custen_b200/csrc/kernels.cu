@@ -255,7 +255,7 @@ int launch_band(const Band& b, cudaStream_t st)
 
     if (b.weno)
     {
-        launch_tile_instance<false, 2, OpWeno>(a, st);
+        launch_tile_geom<TileWeno, 1, OpWeno>(a, st);
         return PATH_STREAM_TILE;
     }
     const bool lodd = (b.L & 1) != 0;

@@ -579,6 +579,8 @@ __global__ void __launch_bounds__(NT + 32, MINB) stream_tile_kernel(const __grid
 // windows, 256-column strips and two CTAs per SM otherwise.
 struct TileSmall { static constexpr int NT = 256, SR = 8, NS = 3, MAXCPS = 2; };
 struct TileBig { static constexpr int NT = 512, SR = 16, NS = 3, MAXCPS = 1; };
+// WENO is compute-bound (18 single-precision powf per point): as many warps as the register file allows.
+struct TileWeno { static constexpr int NT = 736, SR = 8, NS = 2, MAXCPS = 1; };
 
 struct LaunchGeom
 {
