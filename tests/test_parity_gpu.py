@@ -247,3 +247,29 @@ def test_reference_kernels_at_config2_size():
     ref = ol.ref_sweep("Xp", inp, np.zeros_like(inp), coef, tiles=2, block=(32, 32), H=9, L=4, R=4)
     got = gu.run_ours(c, inp, out_init=np.zeros_like(inp))
     assert ol.count_diff(got, ref) == 0
+
+
+@pytest.mark.parametrize("variant,nx,ny,kw", [
+    ("XYp", 1300, 96, dict(H=3, L=1, R=1, V=3, T=1, B=1)),          # 512 + 512 + 276-column strips, periodic wrap on a partial strip
+    ("XYp", 1280, 40, dict(H=5, L=2, R=2, V=5, T=2, B=2)),
+    ("Xp", 1300, 33, dict(H=9, L=4, R=4)),
+    ("Xnp", 1038, 17, dict(H=5, L=2, R=2)),
+    ("Yp", 770, 300, dict(V=9, T=4, B=4)),
+    ("XYnp", 1100, 70, dict(H=5, L=2, R=2, V=5, T=2, B=2)),
+    ("XYpFun", 1300, 50, dict(H=3, L=1, R=1, V=3, T=1, B=1, fun="cubic_xy")),
+    ("XYnpFun", 600, 9, dict(H=3, L=1, R=1, V=3, T=1, B=1, fun="weighted_xy")),
+    ("XYp", 64, 6, dict(H=5, L=2, R=2, V=5, T=2, B=2)),             # fewer rows than a stage
+    ("Yp", 16, 12, dict(V=9, T=4, B=4)),                            # smallest width the TMA path takes
+    ("XYp", 518, 64, dict(H=7, L=3, R=3, V=3, T=1, B=1)),           # odd L on a partial second strip (tile family)
+    ("Xp", 2050, 8, dict(H=7, L=3, R=3)),
+])
+def test_ragged_grids_on_the_streaming_path(variant, nx, ny, kw):
+    """Grids the reference cannot run (sizes not multiples of its blocks): strips that do not fill, wrap pieces on a
+    partial strip, bands shorter than a stage.  Oracle only."""
+    H, V = kw.get("H", 1), kw.get("V", 1)
+    coef = np.random.default_rng(nx + ny).uniform(-1, 1, H * V)
+    c = cases._c("ragged", variant, nx, ny, 1, (2, 1), coef, **kw)
+    inp = cases.case_input(c)
+    got, path, _ = gu.run_ours(c, inp, return_path=True)
+    assert path.startswith("stream"), path
+    assert ol.count_diff(got, _oracle(c, inp)) == 0
