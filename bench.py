@@ -252,6 +252,13 @@ def run_ours(args, rank, world, local_rank):
     import custen_b200.slab as slab
 
     torch.cuda.set_device(local_rank)
+    # keep this rank (and the pinned buffers it allocates) on the CPUs / memory next to its GPU
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+    except Exception:
+        pass
     dist = None
     if world > 1:
         import torch.distributed as dist
