@@ -33,7 +33,12 @@ $(LIBDIR)/libcusten_b200.so: $(CORE_OBJ) $(CABI_OBJ)
 	$(NVCC) $(ARCH) -shared -o $@ $(CORE_OBJ) $(CABI_OBJ)
 
 # the re-hosted Cahn-Hilliard driver program (reference: cuPentSpeedUp/cuPentCahnADITiming)
-examples: examples/bin/cuPentCahnADI
+examples: examples/bin/cuPentCahnADI examples/bin/registered_fun
+
+# a user program against the C++ drop-in API and the static archive, with a registered __device__ function
+examples/bin/registered_fun: examples/registered_fun.cu $(LIBDIR)/libcuSten.a $(HEADERS)
+	@mkdir -p examples/bin
+	$(NVCC) $(ARCH) -O3 -std=c++17 -rdc=true -o $@ $< $(LIBDIR)/libcuSten.a
 
 examples/bin/cuPentCahnADI: examples/cuPentCahnADI.cu $(LIBDIR)/libcusten_b200.so
 	@mkdir -p examples/bin

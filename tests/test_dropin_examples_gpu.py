@@ -36,3 +36,14 @@ def test_reference_example_prints_the_same_with_the_new_library(name):
         assert min(diff) >= len(la) - 8 * 512
         return
     assert not diff, f"{len(diff)} of {len(la)} lines differ, first: {la[diff[0]]!r} vs {lb[diff[0]]!r}"
+
+
+def test_user_program_with_registered_function():
+    """examples/registered_fun.cu: a user translation unit linked against libcuSten.a; its __device__ function once as
+    an opaque pointer, once registered with CUSTEN_REGISTER_FUN_XY.  The program exits 0 iff both give the same bits."""
+    exe = os.path.join(ROOT, "examples", "bin", "registered_fun")
+    if not os.path.exists(exe):
+        pytest.skip("examples not built (make examples)")
+    r = subprocess.run([exe, "2048"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "bit-identical" in r.stdout
