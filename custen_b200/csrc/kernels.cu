@@ -301,9 +301,9 @@ int launch_band(const Band& b, cudaStream_t st)
         }
     }
     // opaque pointer: no minimum-blocks bound, the callee's register need is unknown until device link
-    if (b.dir == DIR_X) launch_tile_instance<false, 1, OpPtrX>(a, st);
-    else if (b.dir == DIR_Y) launch_tile_instance<false, 1, OpPtrY>(a, st);
-    else launch_tile_instance<false, 1, OpPtrXY>(a, st);
+    if (b.dir == DIR_X) launch_tile_opaque<OpPtrX>(a, st);
+    else if (b.dir == DIR_Y) launch_tile_opaque<OpPtrY>(a, st);
+    else launch_tile_opaque<OpPtrXY>(a, st);
     return PATH_STREAM_TILE;
 }
 

@@ -615,6 +615,17 @@ inline void launch_tile_geom(StreamArgs& a, cudaStream_t st)
     kernel<<<g.grid, g.threads, g.smem, st>>>(a);
 }
 
+// Opaque user functions: their register need is only known at device link, where a kernel compiled for a large CTA
+// (a low per-thread register cap) would fail to link against a register-hungry callee.  So the opaque road stays on
+// 288-thread CTAs (cap 224 registers) and takes as many of them per SM as the occupancy calculator allows.
+struct TileOpq256 { static constexpr int NT = 256, SR = 8, NS = 3, MAXCPS = 3; };
+
+template <class Op>
+inline void launch_tile_opaque(StreamArgs& a, cudaStream_t st)
+{
+    launch_tile_geom<TileOpq256, 1, Op>(a, st);
+}
+
 // BIG selects the wide geometry when the window is at most 3 rows tall (its stages then fit in shared memory).
 template <bool BIG, int MINB, class Op>
 inline void launch_tile_instance(StreamArgs& a, cudaStream_t st)
