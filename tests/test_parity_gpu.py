@@ -202,7 +202,7 @@ def test_public_handle_fields_follow_the_reference_formulas():
     buf.free()
 
 
-@pytest.mark.parametrize("variant,n", [("Xp", 8192), ("XYp", 16384), ("XYnp", 16384), ("XYpFun", 16384)])
+@pytest.mark.parametrize("variant,n", [("Xp", 8192), ("XYp", 16384), ("XYnp", 16384), ("XYpFun", 16384), ("XYpFun", 32768)])
 def test_full_size_properties(variant, n):
     """BASELINE.json sizes: the two independent kernel families agree bit for bit, and periodic sweeps commute
     with a cyclic shift of the grid (checked on the device)."""
