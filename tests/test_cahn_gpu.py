@@ -91,3 +91,18 @@ def test_rehosted_driver_program_runs():
     assert float(r.stdout.split()[0]) > 0.0
     m = re.search(r"mean\(c\) = (\S+), max\|c\| = (\S+)", r.stderr)
     assert m and abs(float(m.group(1))) < 1e-3 and 0.0 < float(m.group(2)) < 1.5
+
+
+@pytest.mark.parametrize("table_rows", [8, 24, 104])
+def test_coefficient_table_refills_do_not_change_results(table_rows):
+    """The solve stages the factor coefficients in shared memory a block of rows at a time; crossing refills
+    (forced here with tiny blocks) must give the same bits as one block."""
+    import custen_b200 as cs
+    c0 = _initial(256, seed=21)
+    want = _ours(c0, 6)
+    cs.load().custen_cahn_set_table_rows(table_rows)
+    try:
+        got = _ours(c0, 6)
+    finally:
+        cs.load().custen_cahn_set_table_rows(4096)
+    assert ol.count_diff(got, want) == 0
