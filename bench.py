@@ -418,6 +418,41 @@ def run_ours(args, rank, world, local_rank):
             del a, b
 
     if world == 1 and not args.no_table:
+        # BASELINE.json config 3 as the reference's callers run it: unified memory, numTiles = 4, through the
+        # prefetch pipeline; offload = DEVICE (tiles stay on the GPU) and offload = HOST (every tile is sent back to
+        # the CPU after its sweep, so each step crosses the host link in both directions)
+        try:
+            from custen_b200.cahn import _DeviceBuffer
+            v3, n3, t3, _ = WORKLOADS["xy_np_16384_t4"]
+            c3, k3 = stencil_args(v3, n3)
+            lib = cs.load()
+            cnt = n3 * n3
+            m_in, m_out, m_w = lib.custen_managed_alloc(cnt * 8), lib.custen_managed_alloc(cnt * 8), lib.custen_managed_alloc(9 * 8)
+            torch.as_tensor(_DeviceBuffer(m_in, cnt), device="cuda").uniform_(-1, 1)
+            torch.as_tensor(_DeviceBuffer(m_out, cnt), device="cuda").zero_()
+            torch.as_tensor(_DeviceBuffer(m_w, 9), device="cuda").copy_(torch.from_numpy(np.ascontiguousarray(c3)).cuda())
+            torch.cuda.synchronize()
+            s3 = cs.Stencil2D(v3, n3, n3, m_out, m_in, m_w, numTiles=t3, **k3)
+            res3 = {}
+            for name, off, reps in (("offload_DEVICE", cs.DEVICE, 10), ("offload_HOST", cs.HOST, 3)):
+                s3.compute(off)
+                cs.device_synchronize()
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    s3.compute(off)
+                cs.device_synchronize()
+                dt3 = (time.perf_counter() - t0) / reps
+                res3[name] = {"gpoints_per_s": round(n3 * n3 / dt3 / 1e9, 2), "ms_per_step": round(dt3 * 1e3, 3)}
+            res3["offload_HOST"]["host_link_gbs_each_way"] = round(2 * cnt * 8 / (res3["offload_HOST"]["ms_per_step"] * 1e-3) / 1e9, 1)
+            res3["mode"] = s3.mode
+            res3["note"] = "cudaMallocManaged buffers, numTiles = 4 (wall clock around Compute + device sync)"
+            extras["xy_np_16384_t4_unified_memory"] = res3
+            s3.destroy()
+            for pm in (m_in, m_out, m_w):
+                lib.custen_managed_free(pm)
+        except Exception as ex:
+            extras["xy_np_16384_t4_unified_memory"] = {"error": str(ex)}
+
         # BASELINE.json config 5 (and the 512^2 size of config 1): Cahn-Hilliard ADI steps on the re-hosted solver
         from custen_b200.cahn import CahnHilliard
         for ncahn in (512, 4096):
