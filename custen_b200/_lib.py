@@ -34,7 +34,7 @@ _CREATE_TAIL = {
 EXPORTED = (
     [f"custen{op}2D{v}" for v in VARIANTS + ("XYWENOADVp",) for op in ("Create", "Swap", "Destroy", "Compute")]
     + ["custenCheckError", "custen_handle_size", "custen_device_synchronize", "custen_builtin_fun",
-       "custen_last_path", "custen_last_mode", "custen_launch_count", "custen_set_tuning", "custen_set_slab",
+       "custen_last_path", "custen_last_mode", "custen_launch_count", "custen_set_tuning", "custen_set_managed_policy", "custen_set_slab",
        "custen_ipc_export", "custen_ipc_open", "custen_ipc_close", "custen_event_create", "custen_event_record",
        "custen_event_synchronize", "custen_event_elapsed_ms", "custen_event_destroy", "custen_host_alloc",
        "custen_host_free", "custen_managed_alloc", "custen_managed_free", "custen_peer_barrier", "custen_device_alloc",
@@ -79,6 +79,7 @@ def load():
     lib.custen_last_mode.argtypes, lib.custen_last_mode.restype = [_c_void_p], _c_int
     lib.custen_launch_count.argtypes, lib.custen_launch_count.restype = [], ctypes.c_uint64
     lib.custen_set_tuning.argtypes, lib.custen_set_tuning.restype = [_c_int] * 5, None
+    lib.custen_set_managed_policy.argtypes, lib.custen_set_managed_policy.restype = [_c_int], None
     lib.custen_set_slab.argtypes, lib.custen_set_slab.restype = [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int], None
     lib.custen_ipc_export.argtypes, lib.custen_ipc_export.restype = [_c_void_p, _c_void_p, _c_void_p], None
     lib.custen_ipc_open.argtypes, lib.custen_ipc_open.restype = [_c_void_p], ctypes.c_void_p

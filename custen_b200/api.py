@@ -16,7 +16,8 @@ DEVICE = 0  # cuSten/cuSten.h:30
 HOST = 1    # cuSten/cuSten.h:31
 
 PATH_NAMES = {0: "none", 1: "stream_acc", 2: "stream_tile", 3: "fallback", 4: "stream_inline"}
-MODE_NAMES = {0: "resident", 1: "resident_per_tile", 2: "managed_pipeline", 3: "staged"}
+MODE_NAMES = {0: "resident", 1: "resident_per_tile", 2: "managed_pipeline", 3: "staged", 4: "managed_resident",
+              5: "managed_zero_copy"}
 
 
 class cuSten_t(ctypes.Structure):
@@ -134,6 +135,11 @@ def launch_count():
 
 def set_tuning(force_fallback=0, force_tile=0, chunk_rows=0, ctas_per_sm=0, force_opaque=0):
     _lib.load().custen_set_tuning(force_fallback, force_tile, chunk_rows, ctas_per_sm, force_opaque)
+
+
+def set_managed_policy(policy=0):
+    """0: unified-memory grids take the resident / zero-copy roads when they apply; 1: always the prefetch pipeline."""
+    _lib.load().custen_set_managed_policy(int(policy))
 
 
 def set_slab(handle, top, bottom, is_first, is_last):

@@ -131,6 +131,8 @@ void custen_set_tuning(int force_fallback, int force_tile, int chunk_rows, int c
     t.force_opaque = force_opaque;
 }
 
+void custen_set_managed_policy(int policy) { set_managed_policy(policy); }
+
 void custen_set_slab(cuSten_c_handle* h, const double* top, const double* bottom, int is_first, int is_last)
 {
     Plan* p = plan_of(H(h));

@@ -177,6 +177,8 @@ void plan_swap(cuSten_t* h, double* dataInput)
     if (h->boundaryTop && dataInput) set_boundaries(h, dataInput);
 }
 
+static void unadvise(Plan* p, int dev);
+
 static void release_staging(Plan* p)
 {
     for (int s = 0; s < kSlots; ++s)
@@ -208,6 +210,7 @@ void plan_destroy(cuSten_t* h)
         if (p->stage_rows || p->d_coef)
             for (int s = 0; s < 3; ++s) cudaStreamSynchronize(h->streams[s]);
         release_staging(p);
+        if (p->zc_n) unadvise(p, h->deviceNum);
         free(p);
     }
     for (int s = 0; s < h->numStreams; ++s)
@@ -383,12 +386,158 @@ static void prefetch_tile(cuSten_t* h, int t, int dst, cudaStream_t st)
     }
 }
 
-// unified memory: the reference's load / compute / unload rotation, ordered on the device with
-// cudaStreamWaitEvent instead of host-side cudaEventSynchronize / cudaStreamSynchronize.
+// ---- unified memory ------------------------------------------------------------------------------------------------
+// Three roads, chosen per call (custen_set_managed_policy(1) pins the first one):
+//   pipeline  the reference's load / compute / unload rotation over three streams and two events
+//             (2d_xy_p_kernel.cu:561-655), ordered on the device with cudaStreamWaitEvent instead of host-side
+//             cudaEventSynchronize / cudaStreamSynchronize;
+//   resident  offload == DEVICE and every range was last prefetched to this GPU (what the previous DEVICE call
+//             left behind): nothing has to move, so the prefetch calls - which cost more than the sweep itself on
+//             multi-GiB ranges even when they move nothing - are skipped and the grid is swept like device memory.
+//             Pages the CPU touched in between come back through ordinary GPU page faults;
+//   zero-copy offload == HOST: the grid is meant to live on the CPU between sweeps.  Instead of migrating every
+//             tile to the GPU and back (2 x 16 B per point over the host link at page-migration speed), the ranges
+//             are advised "preferred location CPU, accessed by this GPU" and the kernel's own TMA producer reads
+//             the rows over the host link while stores go straight back (8 + 8 B per point at link speed).  Pages
+//             that happen to be on the GPU are read there and sent home by a prefetch behind the kernel.
+
+struct Span
+{
+    const void* p;
+    size_t bytes;
+};
+
+// the unified-memory arrays a sweep touches, as whole ranges (tiles are carved from one array each)
+static int managed_spans(const cuSten_t* h, Span* sp)
+{
+    int n = 0;
+    const size_t bytes = (size_t)h->nx * h->nyTile * h->numTiles * sizeof(double);
+    const void* c[4] = {h->dataInput[0], h->dataOutput[0], h->uVel ? h->uVel[0] : nullptr, h->vVel ? h->vVel[0] : nullptr};
+    for (int k = 0; k < 4; ++k)
+        if (c[k] && classify(c[k]) == MK_MANAGED) sp[n++] = Span{c[k], bytes};
+    return n;
+}
+
+// Where this handle's previous unified-memory call left the arrays (1 = on the GPU, 2 = at home on the CPU under the
+// zero-copy advice).  Kept per handle because the driver offers no cheap residency query; a Swap exchanges in and out,
+// so the comparison ignores order.
+static bool left_at(const Plan* p, const Span* sp, int nsp, int where)
+{
+    if (p->res_where != where || p->res_n != nsp) return false;
+    for (int k = 0; k < nsp; ++k)
+    {
+        bool found = false;
+        for (int j = 0; j < p->res_n; ++j) found |= (p->res_ptr[j] == sp[k].p && p->res_bytes[j] == sp[k].bytes);
+        if (!found) return false;
+    }
+    return true;
+}
+static void note_left_at(Plan* p, const Span* sp, int nsp, int where)
+{
+    p->res_where = where;
+    p->res_n = nsp;
+    for (int k = 0; k < nsp; ++k)
+    {
+        p->res_ptr[k] = sp[k].p;
+        p->res_bytes[k] = sp[k].bytes;
+    }
+}
+
+static void unadvise(Plan* p, int dev)
+{
+    for (int k = 0; k < p->zc_n; ++k)
+    {
+        cudaMemAdvise(p->zc_ptr[k], p->zc_bytes[k], cudaMemAdviseUnsetAccessedBy, dev);
+        cudaMemAdvise(p->zc_ptr[k], p->zc_bytes[k], cudaMemAdviseUnsetPreferredLocation, dev);
+    }
+    cudaGetLastError();  // the caller may already have freed the arrays
+    p->zc_n = 0;
+}
+
+static bool advised(const Plan* p, const Span& s)
+{
+    for (int k = 0; k < p->zc_n; ++k)
+        if (p->zc_ptr[k] == s.p && p->zc_bytes[k] == s.bytes) return true;
+    return false;
+}
+
+static int managed_policy_flag = 0;
+void set_managed_policy(int policy) { managed_policy_flag = policy; }
+
+// The pipeline spreads a call over the three rotating streams; the single-launch roads use streams[0] only.  When
+// one follows the other, streams[0] first waits for whatever the previous call left running on the other two.
+static void join_streams(cuSten_t* h)
+{
+    for (int k = 1; k <= 2; ++k)
+    {
+        cudaEventRecord(h->events[k - 1], h->streams[k]);
+        cudaStreamWaitEvent(h->streams[0], h->events[k - 1], 0);
+    }
+}
+
 static void compute_managed(cuSten_t* h, Plan* p, const double* coef, MemKind kcoef, bool offload)
 {
     const int dev = h->deviceNum;
+    Span sp[kMaxSpans];
+    const int nsp = (managed_policy_flag == 0 && tiles_contiguous(h)) ? managed_spans(h, sp) : 0;
+    const bool spans_complete = nsp > 0;
+
+    if (spans_complete && !offload)
+    {
+        if (left_at(p, sp, nsp, 1))
+        {
+            if (p->last_mode == 2) join_streams(h);
+            if (kcoef == MK_MANAGED) prefetch(coef, (size_t)p->ncoef * sizeof(double), dev, h->streams[0]);
+            compute_resident(h, p, coef);
+            p->last_mode = 4;
+            return;
+        }
+    }
+    if (spans_complete && offload)
+    {
+        int concurrent = 0;
+        cudaDeviceGetAttribute(&concurrent, cudaDevAttrConcurrentManagedAccess, dev);
+        if (concurrent)
+        {
+            bool ok = true;
+            for (int k = 0; k < nsp && ok; ++k)
+            {
+                if (advised(p, sp[k])) continue;
+                ok = cudaMemAdvise(sp[k].p, sp[k].bytes, cudaMemAdviseSetPreferredLocation, cudaCpuDeviceId) == cudaSuccess &&
+                     cudaMemAdvise(sp[k].p, sp[k].bytes, cudaMemAdviseSetAccessedBy, dev) == cudaSuccess;
+                if (ok && p->zc_n < kMaxSpans)
+                {
+                    p->zc_ptr[p->zc_n] = sp[k].p;
+                    p->zc_bytes[p->zc_n] = sp[k].bytes;
+                    ++p->zc_n;
+                }
+            }
+            if (ok)
+            {
+                if (p->last_mode == 2) join_streams(h);
+                if (kcoef == MK_MANAGED) prefetch(coef, (size_t)p->ncoef * sizeof(double), dev, h->streams[0]);
+                cudaStream_t st = h->streams[0];
+                compute_resident(h, p, coef);
+                p->last_mode = 5;
+                // anything that was on the GPU goes home behind the kernel (stream order); once there, the advice
+                // keeps it there
+                if (!left_at(p, sp, nsp, 2))
+                {
+                    for (int k = 0; k < nsp; ++k) prefetch(sp[k].p, sp[k].bytes, cudaCpuDeviceId, st);
+                    note_left_at(p, sp, nsp, 2);
+                }
+                check("Error in unified-memory zero-copy sweep", dev);
+                return;
+            }
+            cudaGetLastError();
+            unadvise(p, dev);
+        }
+    }
+
+    if (p->zc_n) unadvise(p, dev);
     p->last_mode = 2;
+    p->res_where = 0;
+    if (spans_complete && !offload) note_left_at(p, sp, nsp, 1);  // the pipeline below leaves every tile on the GPU
     if (kcoef == MK_MANAGED) prefetch(coef, (size_t)p->ncoef * sizeof(double), dev, h->streams[1]);
     prefetch_tile(h, 0, dev, h->streams[1]);
     cudaEventRecord(h->events[0], h->streams[1]);

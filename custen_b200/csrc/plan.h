@@ -23,6 +23,7 @@ struct Spec
 enum MemKind : int { MK_DEVICE = 0, MK_MANAGED = 1, MK_HOST = 2 };
 
 constexpr int kSlots = 3;  // staging ring depth for host-resident grids
+constexpr int kMaxSpans = 4;  // unified-memory arrays of one handle: in, out, (u, v)
 
 // Private state hung behind the public `streams` array (slot numStreams = magic, the next = Plan*), so that
 // sizeof(cuSten_t) and every public field offset stay as in the reference.
@@ -31,7 +32,16 @@ struct Plan
     Spec spec;
     int ncoef;
     int last_path;           // Path of the most recent launch
-    int last_mode;           // 0 resident single launch, 1 resident per tile, 2 managed pipeline, 3 staged
+    int last_mode;           // 0 resident single launch, 1 resident per tile, 2 managed pipeline, 3 staged,
+                             // 4 managed + already resident, 5 managed + zero-copy over the host link
+    // unified-memory ranges this handle put under "preferred location CPU / accessed by GPU" advice (HOST offload)
+    const void* zc_ptr[kMaxSpans];
+    size_t zc_bytes[kMaxSpans];
+    int zc_n;
+    // where the previous unified-memory call left which arrays: 0 unknown, 1 on the GPU, 2 at home on the CPU
+    const void* res_ptr[kMaxSpans];
+    size_t res_bytes[kMaxSpans];
+    int res_n, res_where;
     // slab extension (multi-GPU layer): rows above / below the grid come from these buffers
     const double* slab_top;
     const double* slab_bottom;
@@ -58,6 +68,9 @@ void plan_destroy(cuSten_t* h);
 void plan_compute(cuSten_t* h, bool offload);
 
 MemKind classify(const void* p);
+// 0 (default): unified-memory grids take the resident / zero-copy roads when they apply; 1: always the reference's
+// prefetch pipeline
+void set_managed_policy(int policy);
 
 // What one launch would cover, for tests of the host logic (see debug_bands in plan.cu).
 struct BandDesc

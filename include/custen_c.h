@@ -93,6 +93,11 @@ int custen_last_path(cuSten_c_handle* pt_cuSten);
 int custen_last_mode(cuSten_c_handle* pt_cuSten);
 uint64_t custen_launch_count(void);              /* kernels launched by this library so far */
 void custen_set_tuning(int force_fallback, int force_tile, int chunk_rows, int ctas_per_sm, int force_opaque);
+/* Unified-memory grids (what the reference requires, cuSten/src/kernels/2d_xy_p_kernel.cu:561-572).  0 (default):
+ * offload == DEVICE skips the prefetches when the previous call left the grid on the GPU; offload == HOST sweeps the
+ * grid in place over the host link (preferred location CPU + accessed-by advice) instead of migrating every tile both
+ * ways.  1: always the reference's prefetch pipeline. */
+void custen_set_managed_policy(int policy);
 
 /* Multi-GPU y-slab layer: the handle's grid is one slab of a taller global grid.  `top` / `bottom` point at the
  * numStenTop rows above / numStenBottom rows below the slab (a local halo buffer filled by an exchange, or a

@@ -109,16 +109,57 @@ KIND_CASES = ["x_p_9pt_random", "x_np_5pt_tiles", "x_np_fun_example", "y_p_9pt_t
               "xy_np_fun_cubic_tiles"]
 
 
-@pytest.mark.parametrize("kind,mode", [("managed", "managed_pipeline"), ("pinned", "staged"), ("pageable", "staged")])
+@pytest.mark.parametrize("kind", ["managed", "managed_reference_pipeline", "pinned", "pageable"])
 @pytest.mark.parametrize("name", KIND_CASES)
 @pytest.mark.parametrize("offload", [cs.DEVICE, cs.HOST])
-def test_memory_kinds_and_offload(name, kind, mode, offload):
+def test_memory_kinds_and_offload(name, kind, offload):
     """Unified memory (what the reference requires), pinned and pageable host grids through the tile scheduler."""
     c = next(x for x in cases.CASES if x["name"] == name)
     inp = cases.case_input(c)
-    got, path, m = gu.run_ours(c, inp, kind=kind, offload=offload, return_path=True)
+    if kind == "managed_reference_pipeline":
+        cs.set_managed_policy(1)
+        kind, mode = "managed", "managed_pipeline"
+    elif kind == "managed":
+        # first call on CPU-initialised unified memory: DEVICE runs the prefetch pipeline, HOST sweeps in place
+        mode = "managed_zero_copy" if offload == cs.HOST else "managed_pipeline"
+    else:
+        mode = "staged"
+    try:
+        got, path, m = gu.run_ours(c, inp, kind=kind, offload=offload, return_path=True)
+    finally:
+        cs.set_managed_policy(0)
     assert m == mode
     assert ol.count_diff(got, _oracle(c, inp)) == 0
+
+
+@pytest.mark.parametrize("name", ["xy_p_cross_tiles", "xy_np_fun_cubic_tiles", "y_p_9pt_tiles", "x_np_5pt_tiles"])
+def test_unified_memory_roads_in_sequence(name):
+    """DEVICE, DEVICE (nothing to move: resident road), HOST (zero-copy + send home), CPU edit, HOST, DEVICE again:
+    every call must give the oracle's sweep of whatever the input array holds at that moment."""
+    c = next(x for x in cases.CASES if x["name"] == name)
+    inp = cases.case_input(c)
+    n = inp.size
+    buf = gu.Buffers("managed", inp, np.full_like(inp, cases.SENTINEL), c["coef"])
+    st = cs.Stencil2D(c["variant"], c["nx"], c["ny"], buf.out, buf.inp, buf.coef, H=c["H"], L=c["L"], R=c["R"], V=c["V"],
+                      T=c["T"], B=c["B"], fun=c["fun"], numCoe=c["numCoe"], numTiles=c["tiles"], block=c["block"])
+    host_in = gu._view(buf.inp, n).reshape(inp.shape)
+    host_out = gu._view(buf.out, n).reshape(inp.shape)
+    seen = []
+    cur = inp.copy()
+    for step, off in enumerate([cs.DEVICE, cs.DEVICE, cs.HOST, cs.HOST, cs.DEVICE, cs.DEVICE]):
+        if step == 3:  # the CPU rewrites the input between two HOST sweeps
+            cur = cur[::-1].copy() * 0.5
+            host_in[:] = cur
+        host_out[:] = cases.SENTINEL
+        st.compute(off)
+        cs.device_synchronize()
+        seen.append(st.mode)
+        assert ol.count_diff(host_out.copy(), _oracle(c, cur)) == 0, (step, st.mode)
+    st.destroy()
+    buf.free()
+    assert seen[0] == "managed_pipeline" and seen[1] == "managed_resident", seen
+    assert seen[2] == seen[3] == "managed_zero_copy", seen
+    assert seen[4] == "managed_pipeline" and seen[5] == "managed_resident", seen
 
 
 @pytest.mark.parametrize("tiles", [1, 2, 4, 8])
