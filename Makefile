@@ -10,7 +10,7 @@ OBJDIR    := build/obj
 LIBDIR    := custen_b200/lib
 
 CORE_SRC  := kernels.cu plan.cu api_cpp.cu
-CABI_SRC  := api_c.cu cahn.cu
+CABI_SRC  := api_c.cu cahn.cu pent_tma.cu
 CORE_OBJ  := $(patsubst %.cu,$(OBJDIR)/%.o,$(CORE_SRC))
 CABI_OBJ  := $(patsubst %.cu,$(OBJDIR)/%.o,$(CABI_SRC))
 HEADERS   := $(wildcard $(SRCDIR)/*.h $(SRCDIR)/*.cuh include/*.h)
@@ -23,6 +23,11 @@ lib: $(LIBDIR)/libcuSten.a $(LIBDIR)/libcusten_b200.so
 $(OBJDIR)/%.o: $(SRCDIR)/%.cu $(HEADERS)
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) -c -o $@ $<
+
+# the TMA-fed pentadiagonal solve relies on the instruction order written in the source (see the file's header)
+$(OBJDIR)/pent_tma.o: $(SRCDIR)/pent_tma.cu $(HEADERS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -Xptxas -O1 -c -o $@ $<
 
 $(LIBDIR)/libcuSten.a: $(CORE_OBJ)
 	@mkdir -p $(LIBDIR)
