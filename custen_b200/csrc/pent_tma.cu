@@ -141,25 +141,20 @@ __device__ __forceinline__ void bwd_row(BwdGroup& q, unsigned rb_cur, unsigned r
     q.r[K] = lds_f64<K * 256>(rb);
     q.c[K] = lds_v2f64<K * 16>(cf);
 }
-template <int K>
+// rows LO .. HI of a group, unrolled at compile time: forward ascending, backward descending
+template <int LO, int HI>
 struct Rows
 {
     static __device__ __forceinline__ void fwd(FwdGroup& q, unsigned a, unsigned b, unsigned c, unsigned z, double& p1, double& p2)
     {
-        Rows<K - 1>::fwd(q, a, b, c, z, p1, p2);   // rows 0 .. K-1 first
-        fwd_row<K>(q, a, b, c, z, p1, p2);
+        fwd_row<LO>(q, a, b, c, z, p1, p2);
+        if constexpr (LO < HI) Rows<LO + 1, HI>::fwd(q, a, b, c, z, p1, p2);
     }
     static __device__ __forceinline__ void bwd(BwdGroup& q, unsigned a, unsigned b, unsigned c, unsigned z, double& p1, double& p2)
     {
-        bwd_row<K>(q, a, b, c, z, p1, p2);         // rows K .. 0, bottom to top
-        Rows<K - 1>::bwd(q, a, b, c, z, p1, p2);
+        bwd_row<HI>(q, a, b, c, z, p1, p2);
+        if constexpr (LO < HI) Rows<LO, HI - 1>::bwd(q, a, b, c, z, p1, p2);
     }
-};
-template <>
-struct Rows<-1>
-{
-    static __device__ __forceinline__ void fwd(FwdGroup&, unsigned, unsigned, unsigned, unsigned, double&, double&) {}
-    static __device__ __forceinline__ void bwd(BwdGroup&, unsigned, unsigned, unsigned, unsigned, double&, double&) {}
 };
 __device__ __forceinline__ void group_first_load(FwdGroup& q, unsigned rb, unsigned cf)
 {
@@ -185,33 +180,79 @@ __device__ __forceinline__ void group_first_load(BwdGroup& q, unsigned rb, unsig
 __device__ __forceinline__ unsigned slot_of(unsigned i) { return i % TSLOTS; }
 __device__ __forceinline__ unsigned parity_of(unsigned i) { return (i / TSLOTS) & 1; }
 
+// A value the optimiser must keep in a register (ptxas would otherwise re-derive shared-memory addresses at every use).
+__device__ __forceinline__ unsigned pinned(unsigned v)
+{
+    unsigned r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
+// One poll of an mbarrier phase (no spinning): its latency can then sit underneath other work.
+__device__ __forceinline__ unsigned mbar_test_parity(unsigned bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+
 // Math warp, one sweep over the ngroups = nrows / TG row groups.  FWD: top to bottom, 4 coefficients per row; !FWD:
-// bottom to top, 2 per row.
+// bottom to top, 2 per row.  Slot indices and barrier parities advance incrementally; the barrier of the group after
+// next is polled in the middle of a group so that the poll's latency is not paid between two groups.
 template <bool FWD>
 __device__ __forceinline__ void math_sweep(unsigned sdata, unsigned scoef, unsigned full, unsigned done, int ngroups, int lane,
                                            unsigned zero, unsigned& it)
 {
     typedef typename std::conditional<FWD, FwdGroup, BwdGroup>::type Group;
+    const unsigned b_rb = pinned(sdata + lane * 8), b_cf = pinned(scoef), b_full = pinned(full), b_done = pinned(done);
     double p1 = 0.0, p2 = 0.0;
     Group q;
-    const unsigned end = it + ngroups;
-    mbar_wait_parity(full + 8 * slot_of(it), parity_of(it));
-    group_first_load(q, sdata + slot_of(it) * (TG * 256) + lane * 8, scoef + slot_of(it) * (TG * 32));
-    for (; it < end; ++it)
+    unsigned s_cur = slot_of(it), ph_cur = parity_of(it);
+    mbar_wait_parity(b_full + 8 * s_cur, ph_cur);
+    group_first_load(q, b_rb + s_cur * (TG * 256), b_cf + s_cur * (TG * 32));
+    unsigned s_nxt = s_cur + 1 == TSLOTS ? 0 : s_cur + 1;
+    unsigned ph_nxt = s_cur + 1 == TSLOTS ? ph_cur ^ 1 : ph_cur;
+    unsigned landed = ngroups > 1 ? mbar_test_parity(b_full + 8 * s_nxt, ph_nxt) : 1u;
+    for (int g = 0; g < ngroups; ++g)
     {
         // the next group's copy must have landed: its rows are fetched underneath this group's chain.  (After the last
         // group the fetches re-read the current slot; the values are not used.)
-        const unsigned nx = it + 1 < end ? it + 1 : it;
-        if (it + 1 < end) mbar_wait_parity(full + 8 * slot_of(nx), parity_of(nx));
-        const unsigned rb_cur = sdata + slot_of(it) * (TG * 256) + lane * 8;
-        const unsigned rb_nxt = sdata + slot_of(nx) * (TG * 256) + lane * 8;
-        const unsigned cf_nxt = scoef + slot_of(nx) * (TG * 32);
-        if constexpr (FWD) Rows<TG - 1>::fwd(q, rb_cur, rb_nxt, cf_nxt, zero, p1, p2);
-        else Rows<TG - 1>::bwd(q, rb_cur, rb_nxt, cf_nxt, zero, p1, p2);
+        const bool has_next = g + 1 < ngroups;
+        if (has_next && !landed) mbar_wait_parity(b_full + 8 * s_nxt, ph_nxt);
+        const unsigned s_src = has_next ? s_nxt : s_cur;
+        const unsigned rb_cur = b_rb + s_cur * (TG * 256);
+        const unsigned rb_nxt = b_rb + s_src * (TG * 256);
+        const unsigned cf_nxt = b_cf + s_src * (TG * 32);
+        const unsigned s_nn = s_nxt + 1 == TSLOTS ? 0 : s_nxt + 1;
+        const unsigned ph_nn = s_nxt + 1 == TSLOTS ? ph_nxt ^ 1 : ph_nxt;
+        if constexpr (FWD)
+        {
+            Rows<0, TG / 2 - 1>::fwd(q, rb_cur, rb_nxt, cf_nxt, zero, p1, p2);
+            landed = mbar_test_parity(b_full + 8 * s_nn, ph_nn);
+            Rows<TG / 2, TG - 1>::fwd(q, rb_cur, rb_nxt, cf_nxt, zero, p1, p2);
+        }
+        else
+        {
+            Rows<TG / 2, TG - 1>::bwd(q, rb_cur, rb_nxt, cf_nxt, zero, p1, p2);
+            landed = mbar_test_parity(b_full + 8 * s_nn, ph_nn);
+            Rows<0, TG / 2 - 1>::bwd(q, rb_cur, rb_nxt, cf_nxt, zero, p1, p2);
+        }
         // results -> async proxy (the tensor store reads them), then tell the copy warp
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(done + 8 * slot_of(it)) : "memory");
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(b_done + 8 * s_cur) : "memory");
+        s_cur = s_nxt;
+        ph_cur = ph_nxt;
+        s_nxt = s_nn;
+        ph_nxt = ph_nn;
     }
+    it += ngroups;
 }
 
 // Copy lane, one sweep.  Group g of the sweep is the CTA's group i0 + g; its rows start at row_of(g).

@@ -22,10 +22,12 @@ def _initial(n, seed=0):
     return np.random.default_rng(seed).uniform(-0.1, 0.1, size=(n, n))
 
 
-def _ours(c0, nsteps, lx=LX, solver=0):
-    """solver 0: the TMA-fed pentadiagonal solve (default), 1: the cp.async ring version."""
+def _ours(c0, nsteps, lx=LX, solver=0, fused=1):
+    """solver 0: the TMA-fed pentadiagonal solve (default), 1: the cp.async ring version.
+    fused 1: right-hand side in one pass (default), 0: findCBar + cuStenCompute2DXYp / XYpFun + findRHS."""
     import custen_b200 as cs
     cs.load().custen_cahn_set_solver(solver)
+    cs.load().custen_cahn_set_fused(fused)
     try:
         s = CahnHilliard(c0.shape[0], lx=lx)
         s.set_field(c0)
@@ -34,18 +36,19 @@ def _ours(c0, nsteps, lx=LX, solver=0):
         s.destroy()
     finally:
         cs.load().custen_cahn_set_solver(0)
+        cs.load().custen_cahn_set_fused(1)
     return out
 
 
-@pytest.mark.parametrize("solver", [0, 1])
+@pytest.mark.parametrize("solver,fused", [(0, 1), (1, 1), (0, 0), (1, 0)])
 @pytest.mark.parametrize("n,steps", [(64, 5), (256, 25), (512, 10)])
-def test_bit_exact_against_reference_gpu_solver(n, steps, solver):
+def test_bit_exact_against_reference_gpu_solver(n, steps, solver, fused):
     c0 = _initial(n, seed=n)
     ref = ol.ref_cahn_run(c0, steps, LX)
     if ref is None:
         pytest.skip("reference GPU solver not built")
     ref_field, _ = ref
-    got = _ours(c0, steps, solver=solver)
+    got = _ours(c0, steps, solver=solver, fused=fused)
     diff = ol.count_diff(got, ref_field)
     rel = np.max(np.abs(got - ref_field)) / np.max(np.abs(ref_field))
     assert rel < 1e-13, rel
@@ -122,5 +125,16 @@ def test_tma_and_ring_solves_agree(n):
     c0 = _initial(n, seed=5 * n)
     a = _ours(c0, 4, solver=0)
     b = _ours(c0, 4, solver=1)
+    assert np.isfinite(a).all()
+    assert ol.count_diff(a, b) == 0
+
+
+@pytest.mark.parametrize("n", [64, 100, 136, 512, 2048])
+def test_fused_right_hand_side_matches_the_engine_path(n):
+    """k_rhs_fused (one pass) against findCBar + the two stencils through cuStenCompute2D* + findRHS: same bits,
+    including grids that are not a multiple of the 32 x 32 tile."""
+    c0 = _initial(n, seed=9 * n)
+    a = _ours(c0, 5, fused=1)
+    b = _ours(c0, 5, fused=0)
     assert np.isfinite(a).all()
     assert ol.count_diff(a, b) == 0
