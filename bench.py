@@ -466,15 +466,24 @@ def run_ours(args, rank, world, local_rank):
         # BASELINE.json config 5 (and the 512^2 size of config 1): Cahn-Hilliard ADI steps on the re-hosted solver
         from custen_b200.cahn import CahnHilliard
         for ncahn in (512, 4096):
-            sol = CahnHilliard(ncahn, device=local_rank)
-            sol.set_field(np.random.default_rng(0).uniform(-0.1, 0.1, (ncahn, ncahn)))
-            sol.step(3)
-            ms_step = sol.time_steps(20)
-            sol.destroy()
-            extras[f"cahn_hilliard_{ncahn}"] = {"ms_per_step": round(ms_step, 4),
-                                               "mpoint_steps_per_s": round(ncahn * ncahn / ms_step / 1e3, 1),
-                                               "note": "custen_cahn_step: 2 stencils + 2 cyclic pentadiagonal ADI solves per step, "
-                                                       "bit-identical to the reference GPU solver (tests/test_cahn_gpu.py)"}
+            res = {}
+            # default: fused right-hand-side pass + TMA-fed solve; engine path: findCBar, cuStenCompute2DXYp / XYpFun and
+            # findRHS as separate passes (the reference driver's structure) with the cp.async ring solve
+            for key, fused, solver in (("ms_per_step", 1, 0), ("engine_path_ms_per_step", 0, 1)):
+                lib = cs.load()
+                lib.custen_cahn_set_fused(fused)
+                lib.custen_cahn_set_solver(solver)
+                sol = CahnHilliard(ncahn, device=local_rank)
+                sol.set_field(np.random.default_rng(0).uniform(-0.1, 0.1, (ncahn, ncahn)))
+                sol.step(3)
+                res[key] = round(sol.time_steps(20), 4)
+                sol.destroy()
+            cs.load().custen_cahn_set_fused(1)
+            cs.load().custen_cahn_set_solver(0)
+            res["mpoint_steps_per_s"] = round(ncahn * ncahn / res["ms_per_step"] / 1e3, 1)
+            res["note"] = ("custen_cahn_step: right-hand side (2 stencils) + 2 cyclic pentadiagonal ADI solves per step, "
+                           "bit-identical to the reference GPU solver on both roads (tests/test_cahn_gpu.py)")
+            extras[f"cahn_hilliard_{ncahn}"] = res
 
     cpu = None
     if world == 1 and not args.no_cpu:

@@ -28,8 +28,9 @@ namespace custen_cahn {
 //     finished reading it, TLAG groups after it was issued.
 // Rows 0, 1 (forward) and m-1, m-2 (backward) need no special code: their missing terms have zero coefficients in the
 // tables and x - 0*y is exact, so the operation sequence per row is the reference's (cuPentBatch.cu:153-195).
-constexpr int TSLOTS = 32;      // slots in the ring (4608 B each)
-constexpr int TLAG = 8;         // stores that may still be reading their slot
+constexpr int TW = 8;           // rows held in registers by the math warp
+constexpr int TSLOTS = 16;      // slots in the ring (9 KB each)
+constexpr int TLAG = 4;         // stores that may still be reading their slot
 constexpr int TAHEAD = TSLOTS - TLAG;
 constexpr size_t TMA_SMEM = (size_t)TSLOTS * (TG * 32 + TG * 4) * sizeof(double) + 2 * TSLOTS * sizeof(unsigned long long);
 
@@ -100,79 +101,89 @@ __device__ __forceinline__ unsigned after(unsigned addr, double x, unsigned zero
     return a;
 }
 
-// Registers of one group of rows: right-hand sides and coefficients.
-struct FwdGroup
+// Registers of the math warp: a rolling window of TW rows (right-hand sides and coefficients).  Row K of a group sits
+// in window position K % TW (forward; backward: (TG - 1 - K) % TW); once solved, its registers take the row TW
+// positions further along the sweep, from the current slot or, near the end of the group, from the next one.
+struct FwdWin
 {
-    double2 c0[TG], c1[TG];  // {ds, dl}, {d, 1/d}
-    double r[TG];
+    double2 c0[TW], c1[TW];  // {ds, dl}, {d, 1/d}
+    double r[TW];
 };
-struct BwdGroup
+struct BwdWin
 {
-    double2 c[TG];           // {du, dw}
-    double r[TG];
+    double2 c[TW];           // {du, dw}
+    double r[TW];
+};
+struct Addr
+{
+    unsigned rb_cur, rb_nxt;   // this lane's column in the current / next slot's rows
+    unsigned cf_cur, cf_nxt;   // coefficient rows of the current / next slot
 };
 
-// Row K of a group: solve it, store the result into the current slot (rb_cur), then fetch row K of the next group
-// (rb_nxt / cf_nxt) into the registers row K just vacated.
 template <int K>
-__device__ __forceinline__ void fwd_row(FwdGroup& q, unsigned rb_cur, unsigned rb_nxt, unsigned cf_nxt, unsigned zero, double& p1,
-                                        double& p2)
+__device__ __forceinline__ void fwd_row(FwdWin& q, const Addr& a, unsigned zero, double& p1, double& p2)
 {
+    constexpr int S = K % TW;
     // cuPentBatch.cu:153-172
-    const double x = div_by(q.r[K] - q.c0[K].x * p2 - q.c0[K].y * p1, q.c1[K].x, q.c1[K].y);
-    sts_f64<K * 256>(rb_cur, x);
+    const double x = div_by(q.r[S] - q.c0[S].x * p2 - q.c0[S].y * p1, q.c1[S].x, q.c1[S].y);
+    sts_f64<K * 256>(a.rb_cur, x);
     p2 = p1;
     p1 = x;
-    const unsigned rb = after(rb_nxt, x, zero), cf = after(cf_nxt, x, zero);
-    q.r[K] = lds_f64<K * 256>(rb);
-    q.c0[K] = lds_v2f64<K * 32>(cf);
-    q.c1[K] = lds_v2f64<K * 32 + 16>(cf);
+    constexpr bool SAME = K + TW < TG;
+    constexpr int N = SAME ? K + TW : K + TW - TG;   // row fetched next, in the current or the next slot
+    const unsigned rb = after(SAME ? a.rb_cur : a.rb_nxt, x, zero), cf = after(SAME ? a.cf_cur : a.cf_nxt, x, zero);
+    q.r[S] = lds_f64<N * 256>(rb);
+    q.c0[S] = lds_v2f64<N * 32>(cf);
+    q.c1[S] = lds_v2f64<N * 32 + 16>(cf);
 }
 template <int K>
-__device__ __forceinline__ void bwd_row(BwdGroup& q, unsigned rb_cur, unsigned rb_nxt, unsigned cf_nxt, unsigned zero, double& p1,
-                                        double& p2)
+__device__ __forceinline__ void bwd_row(BwdWin& q, const Addr& a, unsigned zero, double& p1, double& p2)
 {
+    constexpr int S = (TG - 1 - K) % TW;
     // cuPentBatch.cu:176-195; p1 = x[i+1], p2 = x[i+2]
-    const double x = q.r[K] - q.c[K].x * p1 - q.c[K].y * p2;
-    sts_f64<K * 256>(rb_cur, x);
+    const double x = q.r[S] - q.c[S].x * p1 - q.c[S].y * p2;
+    sts_f64<K * 256>(a.rb_cur, x);
     p2 = p1;
     p1 = x;
-    const unsigned rb = after(rb_nxt, x, zero), cf = after(cf_nxt, x, zero);
-    q.r[K] = lds_f64<K * 256>(rb);
-    q.c[K] = lds_v2f64<K * 16>(cf);
+    constexpr bool SAME = K - TW >= 0;
+    constexpr int N = SAME ? K - TW : K - TW + TG;
+    const unsigned rb = after(SAME ? a.rb_cur : a.rb_nxt, x, zero), cf = after(SAME ? a.cf_cur : a.cf_nxt, x, zero);
+    q.r[S] = lds_f64<N * 256>(rb);
+    q.c[S] = lds_v2f64<N * 16>(cf);
 }
 // rows LO .. HI of a group, unrolled at compile time: forward ascending, backward descending
 template <int LO, int HI>
 struct Rows
 {
-    static __device__ __forceinline__ void fwd(FwdGroup& q, unsigned a, unsigned b, unsigned c, unsigned z, double& p1, double& p2)
+    static __device__ __forceinline__ void fwd(FwdWin& q, const Addr& a, unsigned z, double& p1, double& p2)
     {
-        fwd_row<LO>(q, a, b, c, z, p1, p2);
-        if constexpr (LO < HI) Rows<LO + 1, HI>::fwd(q, a, b, c, z, p1, p2);
+        fwd_row<LO>(q, a, z, p1, p2);
+        if constexpr (LO < HI) Rows<LO + 1, HI>::fwd(q, a, z, p1, p2);
     }
-    static __device__ __forceinline__ void bwd(BwdGroup& q, unsigned a, unsigned b, unsigned c, unsigned z, double& p1, double& p2)
+    static __device__ __forceinline__ void bwd(BwdWin& q, const Addr& a, unsigned z, double& p1, double& p2)
     {
-        bwd_row<HI>(q, a, b, c, z, p1, p2);
-        if constexpr (LO < HI) Rows<LO, HI - 1>::bwd(q, a, b, c, z, p1, p2);
+        bwd_row<HI>(q, a, z, p1, p2);
+        if constexpr (LO < HI) Rows<LO, HI - 1>::bwd(q, a, z, p1, p2);
     }
 };
-__device__ __forceinline__ void group_first_load(FwdGroup& q, unsigned rb, unsigned cf)
+// the first TW rows of a sweep
+__device__ __forceinline__ void window_first_load(FwdWin& q, unsigned rb, unsigned cf)
 {
 #pragma unroll
-    for (int k = 0; k < TG; ++k)
+    for (int k = 0; k < TW; ++k)
     {
         asm volatile("ld.shared.f64 %0, [%1];" : "=d"(q.r[k]) : "r"(rb + k * 256));
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(q.c0[k].x), "=d"(q.c0[k].y) : "r"(cf + k * 32));
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(q.c1[k].x), "=d"(q.c1[k].y) : "r"(cf + k * 32 + 16));
     }
 }
-__device__ __forceinline__ void group_first_load(BwdGroup& q, unsigned rb, unsigned cf)
+__device__ __forceinline__ void window_first_load(BwdWin& q, unsigned rb, unsigned cf)
 {
 #pragma unroll
-    for (int k = 0; k < TG; ++k)
+    for (int k = 0; k < TW; ++k)   // window position k = row TG - 1 - k
     {
-        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(q.r[k]) : "r"(rb + k * 256));
-        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(q.c[k].x), "=d"(q.c[k].y) : "r"(cf + k * 16));
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(q.r[k]) : "r"(rb + (TG - 1 - k) * 256));
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(q.c[k].x), "=d"(q.c[k].y) : "r"(cf + (TG - 1 - k) * 16));
     }
 }
 
@@ -210,13 +221,13 @@ template <bool FWD>
 __device__ __forceinline__ void math_sweep(unsigned sdata, unsigned scoef, unsigned full, unsigned done, int ngroups, int lane,
                                            unsigned zero, unsigned& it)
 {
-    typedef typename std::conditional<FWD, FwdGroup, BwdGroup>::type Group;
+    typedef typename std::conditional<FWD, FwdWin, BwdWin>::type Window;
     const unsigned b_rb = pinned(sdata + lane * 8), b_cf = pinned(scoef), b_full = pinned(full), b_done = pinned(done);
     double p1 = 0.0, p2 = 0.0;
-    Group q;
+    Window q;
     unsigned s_cur = slot_of(it), ph_cur = parity_of(it);
     mbar_wait_parity(b_full + 8 * s_cur, ph_cur);
-    group_first_load(q, b_rb + s_cur * (TG * 256), b_cf + s_cur * (TG * 32));
+    window_first_load(q, b_rb + s_cur * (TG * 256), b_cf + s_cur * (TG * 32));
     unsigned s_nxt = s_cur + 1 == TSLOTS ? 0 : s_cur + 1;
     unsigned ph_nxt = s_cur + 1 == TSLOTS ? ph_cur ^ 1 : ph_cur;
     unsigned landed = ngroups > 1 ? mbar_test_parity(b_full + 8 * s_nxt, ph_nxt) : 1u;
@@ -227,22 +238,24 @@ __device__ __forceinline__ void math_sweep(unsigned sdata, unsigned scoef, unsig
         const bool has_next = g + 1 < ngroups;
         if (has_next && !landed) mbar_wait_parity(b_full + 8 * s_nxt, ph_nxt);
         const unsigned s_src = has_next ? s_nxt : s_cur;
-        const unsigned rb_cur = b_rb + s_cur * (TG * 256);
-        const unsigned rb_nxt = b_rb + s_src * (TG * 256);
-        const unsigned cf_nxt = b_cf + s_src * (TG * 32);
+        Addr a;
+        a.rb_cur = b_rb + s_cur * (TG * 256);
+        a.rb_nxt = b_rb + s_src * (TG * 256);
+        a.cf_cur = b_cf + s_cur * (TG * 32);
+        a.cf_nxt = b_cf + s_src * (TG * 32);
         const unsigned s_nn = s_nxt + 1 == TSLOTS ? 0 : s_nxt + 1;
         const unsigned ph_nn = s_nxt + 1 == TSLOTS ? ph_nxt ^ 1 : ph_nxt;
         if constexpr (FWD)
         {
-            Rows<0, TG / 2 - 1>::fwd(q, rb_cur, rb_nxt, cf_nxt, zero, p1, p2);
+            Rows<0, TG / 2 - 1>::fwd(q, a, zero, p1, p2);
             landed = mbar_test_parity(b_full + 8 * s_nn, ph_nn);
-            Rows<TG / 2, TG - 1>::fwd(q, rb_cur, rb_nxt, cf_nxt, zero, p1, p2);
+            Rows<TG / 2, TG - 1>::fwd(q, a, zero, p1, p2);
         }
         else
         {
-            Rows<TG / 2, TG - 1>::bwd(q, rb_cur, rb_nxt, cf_nxt, zero, p1, p2);
+            Rows<TG / 2, TG - 1>::bwd(q, a, zero, p1, p2);
             landed = mbar_test_parity(b_full + 8 * s_nn, ph_nn);
-            Rows<0, TG / 2 - 1>::bwd(q, rb_cur, rb_nxt, cf_nxt, zero, p1, p2);
+            Rows<0, TG / 2 - 1>::bwd(q, a, zero, p1, p2);
         }
         // results -> async proxy (the tensor store reads them), then tell the copy warp
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
