@@ -24,11 +24,6 @@ $(OBJDIR)/%.o: $(SRCDIR)/%.cu $(HEADERS)
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) -c -o $@ $<
 
-# the TMA-fed pentadiagonal solve relies on the instruction order written in the source (see the file's header)
-$(OBJDIR)/pent_tma.o: $(SRCDIR)/pent_tma.cu $(HEADERS)
-	@mkdir -p $(OBJDIR)
-	$(NVCC) $(NVFLAGS) -Xptxas -O1 -c -o $@ $<
-
 $(LIBDIR)/libcuSten.a: $(CORE_OBJ)
 	@mkdir -p $(LIBDIR)
 	$(NVCC) --lib $(CORE_OBJ) --output-file $@

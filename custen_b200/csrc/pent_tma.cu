@@ -1,10 +1,11 @@
 // The batched pentadiagonal solve of the Cahn-Hilliard ADI step, fed by the TMA engine (see the design note below).
 //
-// This file is its own translation unit because it is compiled with `-Xptxas -O1` (Makefile): the instruction ORDER
-// written here is the optimisation.  The math warp is alone on its scheduler and issues in order, so the shared-memory
-// traffic of a row has to sit in the idle issue slots between the dependent FP64 operations of the recurrence; at its
-// default level ptxas schedules for latency hiding by other warps and moves all of it behind (or in front of) the
-// chain, where it costs ~13 cycles per row (ncu source view).  At -O1 it keeps the order of the PTX.
+// The math warp of this kernel is alone on its scheduler and issues in order, so the instruction ORDER written here is
+// the optimisation: the shared-memory traffic of a row has to sit in the idle issue slots between the dependent FP64
+// operations of the recurrence.  Left to itself ptxas schedules for latency hiding by other warps and moves all of it
+// behind (or in front of) the chain, where it costs ~13 cycles per row (ncu source view).  Every operation of the math
+// warp is therefore a volatile PTX statement; nvcc and ptxas keep their order (checked with cuobjdump -sass; the same
+// source built with -Xptxas -O1 gives the same order and is ~2 % slower).
 #include "pent_solve.h"
 
 #include <cuda.h>
@@ -32,7 +33,8 @@ constexpr int TW = 8;           // rows held in registers by the math warp
 constexpr int TSLOTS = 16;      // slots in the ring (9 KB each)
 constexpr int TLAG = 4;         // stores that may still be reading their slot
 constexpr int TAHEAD = TSLOTS - TLAG;
-constexpr size_t TMA_SMEM = (size_t)TSLOTS * (TG * 32 + TG * 4) * sizeof(double) + 2 * TSLOTS * sizeof(unsigned long long);
+constexpr size_t TMA_SMEM =
+    (size_t)TSLOTS * (TG * 32 + TG * 4) * sizeof(double) + 2 * TSLOTS * sizeof(unsigned long long) + 32 * sizeof(double);
 
 __device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -69,12 +71,28 @@ __device__ __forceinline__ void mbar_wait_parity(unsigned bar, unsigned parity)
         : "memory");
 }
 
-// Shared-memory accesses of the math warp, as PTX so that their order and their addresses are under control.
-// The warp issues in order and ptxas schedules for latency hiding by other warps, which do not exist here: left alone it
-// issues a group's ~50 shared-memory loads in one clump during which the chain stands still (ncu: 13 cycles per row).
-// The loads of the NEXT group's row k are therefore given a (fake) dependence on the CURRENT group's result x_k -
-// address = base + lo32(x_k) * zero, with `zero` a kernel argument that is 0 at run time but unknown to the compiler -
-// so that they can only be placed behind row k's chain operations, i.e. in the idle issue slots of row k+1's.
+// ---- the math warp ------------------------------------------------------------------------------------------------------
+// Every operation of the math warp is a volatile PTX statement, so the statement order below is the schedule.  It is a
+// software pipeline over sweep positions p (forward: row p of the
+// group, backward: row TG-1-p):
+//     chain operation of position p            (each waits ~8 cycles for its predecessor)
+//     "fillers" of position p-1 in the gaps:   store x[p-1] into its slot, fetch position p-1+TW into the registers
+//                                              position p-1 just vacated, and (forward) the off-chain product of p+1
+// so nothing that depends on a fresh result sits between two chain operations (ncu showed the store and the fetch
+// address of a row serialised behind its own result: 12 cycles per row forward, 10 backward).
+// The tables hold NEGATED coefficients (PTX fma has no operand negation): fma(-a, b, c) == fma(a, -b, c) exactly.
+__device__ __forceinline__ double vfma(double a, double b, double c)
+{
+    double d;
+    asm volatile("fma.rn.f64 %0, %1, %2, %3;" : "=d"(d) : "d"(a), "d"(b), "d"(c));
+    return d;
+}
+__device__ __forceinline__ double vmul(double a, double b)
+{
+    double d;
+    asm volatile("mul.rn.f64 %0, %1, %2;" : "=d"(d) : "d"(a), "d"(b));
+    return d;
+}
 template <int OFF>
 __device__ __forceinline__ double lds_f64(unsigned addr)
 {
@@ -94,96 +112,111 @@ __device__ __forceinline__ void sts_f64(unsigned addr, double v)
 {
     asm volatile("st.shared.f64 [%0+%1], %2;" ::"r"(addr), "n"(OFF), "d"(v) : "memory");
 }
-__device__ __forceinline__ unsigned after(unsigned addr, double x, unsigned zero)
-{
-    unsigned a;
-    asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(a) : "r"((unsigned)__double2loint(x)), "r"(zero), "r"(addr));
-    return a;
-}
 
-// Registers of the math warp: a rolling window of TW rows (right-hand sides and coefficients).  Row K of a group sits
-// in window position K % TW (forward; backward: (TG - 1 - K) % TW); once solved, its registers take the row TW
-// positions further along the sweep, from the current slot or, near the end of the group, from the next one.
+// Rolling window of TW sweep positions held in registers: position p lives in window entry p % TW.
 struct FwdWin
 {
-    double2 c0[TW], c1[TW];  // {ds, dl}, {d, 1/d}
+    double2 c0[TW], c1[TW];  // {-ds, -dl}, {-d, 1/d}
     double r[TW];
 };
 struct BwdWin
 {
-    double2 c[TW];           // {du, dw}
+    double2 c[TW];           // {-du, -dw}
     double r[TW];
 };
 struct Addr
 {
-    unsigned rb_cur, rb_nxt;   // this lane's column in the current / next slot's rows
-    unsigned cf_cur, cf_nxt;   // coefficient rows of the current / next slot
+    unsigned rb_prv, rb_cur, rb_nxt;   // this lane's column in the previous / current / next slot's rows
+    unsigned cf_cur, cf_nxt;           // coefficient rows of the current / next slot
+};
+struct Carry
+{
+    double x1, x2;   // the two most recent results (forward: x[i-1], x[i-2]; backward: x[i+1], x[i+2])
+    double t;        // forward only: r[i] - ds[i] x[i-2] of the position about to be solved
 };
 
-template <int K>
-__device__ __forceinline__ void fwd_row(FwdWin& q, const Addr& a, unsigned zero, double& p1, double& p2)
+template <bool FWD>
+__host__ __device__ constexpr int row_at(int pos) { return FWD ? pos : TG - 1 - pos; }
+
+// Fillers of position P - 1 (P = 0: the last position of the previous group): where its result goes and which
+// position's data its registers take next.
+template <bool FWD, int P>
+struct Fill
 {
-    constexpr int S = K % TW;
-    // cuPentBatch.cu:153-172
-    const double x = div_by(q.r[S] - q.c0[S].x * p2 - q.c0[S].y * p1, q.c1[S].x, q.c1[S].y);
-    sts_f64<K * 256>(a.rb_cur, x);
-    p2 = p1;
-    p1 = x;
-    constexpr bool SAME = K + TW < TG;
-    constexpr int N = SAME ? K + TW : K + TW - TG;   // row fetched next, in the current or the next slot
-    const unsigned rb = after(SAME ? a.rb_cur : a.rb_nxt, x, zero), cf = after(SAME ? a.cf_cur : a.cf_nxt, x, zero);
-    q.r[S] = lds_f64<N * 256>(rb);
-    q.c0[S] = lds_v2f64<N * 32>(cf);
-    q.c1[S] = lds_v2f64<N * 32 + 16>(cf);
+    static constexpr int Q = P - 1;                                  // the position being retired
+    static constexpr int W = (Q + TW) % TW;                          // its window entry
+    static constexpr bool ST_PRV = Q < 0;                            // store into the previous slot
+    static constexpr int ST_ROW = row_at<FWD>(Q < 0 ? TG - 1 : Q);
+    static constexpr int NP = Q + TW;                                // position fetched into entry W
+    static constexpr bool LD_NXT = NP >= TG;                         // ... from the next slot
+    static constexpr int LD_ROW = row_at<FWD>(LD_NXT ? NP - TG : NP);
+};
+
+template <int P>
+__device__ __forceinline__ void fwd_pos(FwdWin& q, const Addr& a, Carry& k)
+{
+    typedef Fill<true, P> F;
+    constexpr int S = P % TW, S1 = (P + 1) % TW;
+    const unsigned rb_ld = F::LD_NXT ? a.rb_nxt : a.rb_cur, cf_ld = F::LD_NXT ? a.cf_nxt : a.cf_cur;
+    // x = (r - ds x2 - dl x1) / d as q = u (1/d), rem = fma(-d, q, u), x = fma(1/d, rem, q)   (cuPentBatch.cu:153-172)
+    const double u = vfma(q.c0[S].y, k.x1, k.t);
+    sts_f64<F::ST_ROW * 256>(F::ST_PRV ? a.rb_prv : a.rb_cur, k.x1);
+    const double tn = vfma(q.c0[S1].x, k.x1, q.r[S1]);              // r - ds x2 of position P + 1
+    const double qq = vmul(u, q.c1[S].y);
+    q.r[F::W] = lds_f64<F::LD_ROW * 256>(rb_ld);
+    const double rem = vfma(qq, q.c1[S].x, u);
+    q.c0[F::W] = lds_v2f64<F::LD_ROW * 32>(cf_ld);
+    const double x = vfma(q.c1[S].y, rem, qq);
+    q.c1[F::W] = lds_v2f64<F::LD_ROW * 32 + 16>(cf_ld);
+    k.x2 = k.x1;
+    k.x1 = x;
+    k.t = tn;
 }
-template <int K>
-__device__ __forceinline__ void bwd_row(BwdWin& q, const Addr& a, unsigned zero, double& p1, double& p2)
+template <int P>
+__device__ __forceinline__ void bwd_pos(BwdWin& q, const Addr& a, Carry& k)
 {
-    constexpr int S = (TG - 1 - K) % TW;
-    // cuPentBatch.cu:176-195; p1 = x[i+1], p2 = x[i+2]
-    const double x = q.r[S] - q.c[S].x * p1 - q.c[S].y * p2;
-    sts_f64<K * 256>(a.rb_cur, x);
-    p2 = p1;
-    p1 = x;
-    constexpr bool SAME = K - TW >= 0;
-    constexpr int N = SAME ? K - TW : K - TW + TG;
-    const unsigned rb = after(SAME ? a.rb_cur : a.rb_nxt, x, zero), cf = after(SAME ? a.cf_cur : a.cf_nxt, x, zero);
-    q.r[S] = lds_f64<N * 256>(rb);
-    q.c[S] = lds_v2f64<N * 16>(cf);
+    typedef Fill<false, P> F;
+    constexpr int S = P % TW;
+    const unsigned rb_ld = F::LD_NXT ? a.rb_nxt : a.rb_cur, cf_ld = F::LD_NXT ? a.cf_nxt : a.cf_cur;
+    // x = (r - du x1) - dw x2   (cuPentBatch.cu:176-195)
+    const double t = vfma(q.c[S].x, k.x1, q.r[S]);
+    sts_f64<F::ST_ROW * 256>(F::ST_PRV ? a.rb_prv : a.rb_cur, k.x1);
+    q.r[F::W] = lds_f64<F::LD_ROW * 256>(rb_ld);
+    const double x = vfma(q.c[S].y, k.x2, t);
+    q.c[F::W] = lds_v2f64<F::LD_ROW * 16>(cf_ld);
+    k.x2 = k.x1;
+    k.x1 = x;
 }
-// rows LO .. HI of a group, unrolled at compile time: forward ascending, backward descending
-template <int LO, int HI>
-struct Rows
+// positions LO .. HI of a group, unrolled at compile time
+template <bool FWD, int LO, int HI>
+struct Positions
 {
-    static __device__ __forceinline__ void fwd(FwdWin& q, const Addr& a, unsigned z, double& p1, double& p2)
+    template <class Win>
+    static __device__ __forceinline__ void run(Win& q, const Addr& a, Carry& k)
     {
-        fwd_row<LO>(q, a, z, p1, p2);
-        if constexpr (LO < HI) Rows<LO + 1, HI>::fwd(q, a, z, p1, p2);
-    }
-    static __device__ __forceinline__ void bwd(BwdWin& q, const Addr& a, unsigned z, double& p1, double& p2)
-    {
-        bwd_row<HI>(q, a, z, p1, p2);
-        if constexpr (LO < HI) Rows<LO, HI - 1>::bwd(q, a, z, p1, p2);
+        if constexpr (FWD) fwd_pos<LO>(q, a, k);
+        else bwd_pos<LO>(q, a, k);
+        if constexpr (LO < HI) Positions<FWD, LO + 1, HI>::run(q, a, k);
     }
 };
-// the first TW rows of a sweep
+// the first TW positions of a sweep
 __device__ __forceinline__ void window_first_load(FwdWin& q, unsigned rb, unsigned cf)
 {
 #pragma unroll
-    for (int k = 0; k < TW; ++k)
+    for (int p = 0; p < TW; ++p)
     {
-        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(q.r[k]) : "r"(rb + k * 256));
-        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(q.c0[k].x), "=d"(q.c0[k].y) : "r"(cf + k * 32));
-        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(q.c1[k].x), "=d"(q.c1[k].y) : "r"(cf + k * 32 + 16));
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(q.r[p]) : "r"(rb + p * 256));
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(q.c0[p].x), "=d"(q.c0[p].y) : "r"(cf + p * 32));
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(q.c1[p].x), "=d"(q.c1[p].y) : "r"(cf + p * 32 + 16));
     }
 }
 __device__ __forceinline__ void window_first_load(BwdWin& q, unsigned rb, unsigned cf)
 {
 #pragma unroll
-    for (int k = 0; k < TW; ++k)   // window position k = row TG - 1 - k
+    for (int p = 0; p < TW; ++p)
     {
-        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(q.r[k]) : "r"(rb + (TG - 1 - k) * 256));
-        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(q.c[k].x), "=d"(q.c[k].y) : "r"(cf + (TG - 1 - k) * 16));
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(q.r[p]) : "r"(rb + (TG - 1 - p) * 256));
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(q.c[p].x), "=d"(q.c[p].y) : "r"(cf + (TG - 1 - p) * 16));
     }
 }
 
@@ -213,58 +246,67 @@ __device__ __forceinline__ unsigned mbar_test_parity(unsigned bar, unsigned pari
         : "memory");
     return ok;
 }
+// results of a group -> async proxy (the tensor store reads them), then tell the copy warp
+__device__ __forceinline__ void publish(unsigned done_bar)
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(done_bar) : "memory");
+}
 
 // Math warp, one sweep over the ngroups = nrows / TG row groups.  FWD: top to bottom, 4 coefficients per row; !FWD:
-// bottom to top, 2 per row.  Slot indices and barrier parities advance incrementally; the barrier of the group after
-// next is polled in the middle of a group so that the poll's latency is not paid between two groups.
+// bottom to top, 2 per row.  The result of a group's last position is stored by the first position of the next group
+// (software pipeline), so a group is published one position late; `dummy` is a 256-byte row that takes the store
+// of the (non-existent) position before the first one.
 template <bool FWD>
-__device__ __forceinline__ void math_sweep(unsigned sdata, unsigned scoef, unsigned full, unsigned done, int ngroups, int lane,
-                                           unsigned zero, unsigned& it)
+__device__ __forceinline__ void math_sweep(unsigned sdata, unsigned scoef, unsigned full, unsigned done, unsigned dummy,
+                                           int ngroups, int lane, unsigned& it)
 {
     typedef typename std::conditional<FWD, FwdWin, BwdWin>::type Window;
     const unsigned b_rb = pinned(sdata + lane * 8), b_cf = pinned(scoef), b_full = pinned(full), b_done = pinned(done);
-    double p1 = 0.0, p2 = 0.0;
+    constexpr int LAST_ROW = row_at<FWD>(TG - 1);
     Window q;
     unsigned s_cur = slot_of(it), ph_cur = parity_of(it);
     mbar_wait_parity(b_full + 8 * s_cur, ph_cur);
     window_first_load(q, b_rb + s_cur * (TG * 256), b_cf + s_cur * (TG * 32));
+    Carry k;
+    k.x1 = k.x2 = 0.0;
+    k.t = 0.0;
+    if constexpr (FWD) k.t = vfma(q.c0[0].x, 0.0, q.r[0]);
     unsigned s_nxt = s_cur + 1 == TSLOTS ? 0 : s_cur + 1;
     unsigned ph_nxt = s_cur + 1 == TSLOTS ? ph_cur ^ 1 : ph_cur;
     unsigned landed = ngroups > 1 ? mbar_test_parity(b_full + 8 * s_nxt, ph_nxt) : 1u;
+    unsigned rb_prv = dummy + lane * 8 - LAST_ROW * 256;   // position -1 of the sweep "stores" into the dummy row
+    unsigned done_prv = 0;
     for (int g = 0; g < ngroups; ++g)
     {
-        // the next group's copy must have landed: its rows are fetched underneath this group's chain.  (After the last
-        // group the fetches re-read the current slot; the values are not used.)
+        // the next group's copy must have landed: its first rows are fetched underneath this group's chain.  (After the
+        // last group the fetches re-read the current slot; the values are not used.)
         const bool has_next = g + 1 < ngroups;
         if (has_next && !landed) mbar_wait_parity(b_full + 8 * s_nxt, ph_nxt);
         const unsigned s_src = has_next ? s_nxt : s_cur;
         Addr a;
+        a.rb_prv = rb_prv;
         a.rb_cur = b_rb + s_cur * (TG * 256);
         a.rb_nxt = b_rb + s_src * (TG * 256);
         a.cf_cur = b_cf + s_cur * (TG * 32);
         a.cf_nxt = b_cf + s_src * (TG * 32);
         const unsigned s_nn = s_nxt + 1 == TSLOTS ? 0 : s_nxt + 1;
         const unsigned ph_nn = s_nxt + 1 == TSLOTS ? ph_nxt ^ 1 : ph_nxt;
-        if constexpr (FWD)
-        {
-            Rows<0, TG / 2 - 1>::fwd(q, a, zero, p1, p2);
-            landed = mbar_test_parity(b_full + 8 * s_nn, ph_nn);
-            Rows<TG / 2, TG - 1>::fwd(q, a, zero, p1, p2);
-        }
-        else
-        {
-            Rows<TG / 2, TG - 1>::bwd(q, a, zero, p1, p2);
-            landed = mbar_test_parity(b_full + 8 * s_nn, ph_nn);
-            Rows<0, TG / 2 - 1>::bwd(q, a, zero, p1, p2);
-        }
-        // results -> async proxy (the tensor store reads them), then tell the copy warp
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(b_done + 8 * s_cur) : "memory");
+        Positions<FWD, 0, 0>::run(q, a, k);                 // ... which also stores the previous group's last result
+        if (g > 0) publish(done_prv);
+        Positions<FWD, 1, TG / 2 - 1>::run(q, a, k);
+        landed = mbar_test_parity(b_full + 8 * s_nn, ph_nn);
+        Positions<FWD, TG / 2, TG - 1>::run(q, a, k);
+        rb_prv = a.rb_cur;
+        done_prv = b_done + 8 * s_cur;
         s_cur = s_nxt;
         ph_cur = ph_nxt;
         s_nxt = s_nn;
         ph_nxt = ph_nn;
     }
+    // the sweep's last result is still in a register
+    sts_f64<LAST_ROW * 256>(rb_prv, k.x1);
+    publish(done_prv);
     it += ngroups;
 }
 
@@ -303,12 +345,12 @@ __device__ __forceinline__ void copy_sweep(const CUtensorMap* tm, const double* 
 // The tensor covers all nrows = m + 2 rows of the array (nrows % TG == 0 and nBatch % 32 == 0 are required, so every box
 // is in bounds: the copy engine faults on a store that reaches outside the tensor, tools/tma_probe.cu).  The two rows
 // below the reduced system (the last two unknowns of the cyclic system, handled by k_solve_end) pass through unchanged:
-// tabF holds {0, 0, 1, 1} for them (x = rb / 1), tabB holds {0, 0} for them and for row m-1, {du, 0} for row m-2.
-// tabF: {ds, dl, d, 1/d} per row (zeros where the recurrence has no term); tabB: {du, dw} per row in the order the
+// tabF holds {0, 0, -1, 1} for them (x = rb / 1), tabB holds {0, 0} for them and for row m-1, {-du, 0} for row m-2.
+// tabF: {-ds, -dl, -d, 1/d} per row (zeros where the recurrence has no term); tabB: {-du, -dw} per row in the order the
 // backward sweep visits the groups: entry TG j + k = row nrows - TG (j+1) + k.
 // (x - 0*y is exact; the one representable difference to skipping the term is that a -0.0 may come back as +0.0.)
 __global__ void __launch_bounds__(64) k_pent_solve_tma(const __grid_constant__ CUtensorMap tm, const double* __restrict__ tabF,
-                                                       const double* __restrict__ tabB, int nrows, unsigned zero)
+                                                       const double* __restrict__ tabB, int nrows)
 {
     extern __shared__ __align__(128) unsigned char tma_smem[];
     double (*sdata)[TG * 32] = reinterpret_cast<double (*)[TG * 32]>(tma_smem);
@@ -316,6 +358,7 @@ __global__ void __launch_bounds__(64) k_pent_solve_tma(const __grid_constant__ C
     unsigned long long* full =
         reinterpret_cast<unsigned long long*>(tma_smem + (size_t)TSLOTS * (TG * 32 + TG * 4) * sizeof(double));
     unsigned long long* done = full + TSLOTS;
+    double* dummy = reinterpret_cast<double*>(done + TSLOTS);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int sys0 = blockIdx.x * 32;
     const int ngroups = nrows / TG;
@@ -333,8 +376,9 @@ __global__ void __launch_bounds__(64) k_pent_solve_tma(const __grid_constant__ C
     if (warp == 0)
     {
         const unsigned a_data = smem_addr(sdata), a_coef = smem_addr(scoef), a_full = smem_addr(full), a_done = smem_addr(done);
-        math_sweep<true>(a_data, a_coef, a_full, a_done, ngroups, lane, zero, it);
-        math_sweep<false>(a_data, a_coef, a_full, a_done, ngroups, lane, zero, it);
+        const unsigned a_dummy = smem_addr(dummy);
+        math_sweep<true>(a_data, a_coef, a_full, a_done, a_dummy, ngroups, lane, it);
+        math_sweep<false>(a_data, a_coef, a_full, a_done, a_dummy, ngroups, lane, it);
     }
     else if (lane == 0)
     {
@@ -352,15 +396,15 @@ __global__ void k_build_tables(const double* __restrict__ ds, const double* __re
     if (i >= trows) return;
     // forward, row i
     const bool in = i < m;
-    tabF[4 * i + 0] = (in && i >= 2) ? ds[i] : 0.0;
-    tabF[4 * i + 1] = (in && i >= 1) ? dl[i] : 0.0;
-    tabF[4 * i + 2] = in ? d[i] : 1.0;
+    tabF[4 * i + 0] = (in && i >= 2) ? -ds[i] : 0.0;
+    tabF[4 * i + 1] = (in && i >= 1) ? -dl[i] : 0.0;
+    tabF[4 * i + 2] = in ? -d[i] : -1.0;
     tabF[4 * i + 3] = in ? rinv[i] : 1.0;
     // backward, entry i = group j, position k -> row trows - TG (j+1) + k
     const int j = i / TG, k = i % TG;
     const int row = trows - TG * (j + 1) + k;
-    tabB[2 * i + 0] = (row >= 0 && row <= m - 2) ? du[row] : 0.0;
-    tabB[2 * i + 1] = (row >= 0 && row <= m - 3) ? dw[row] : 0.0;
+    tabB[2 * i + 0] = (row >= 0 && row <= m - 2) ? -du[row] : 0.0;
+    tabB[2 * i + 1] = (row >= 0 && row <= m - 3) ? -dw[row] : 0.0;
 }
 
 // 2-D tensor map over the interleaved right-hand sides: dimension 0 = system (nBatch, contiguous), dimension 1 = row
@@ -411,7 +455,7 @@ bool pent_tma_solve(double* data, int nBatch, int n, const double* tabF, const d
         cudaFuncSetAttribute(k_pent_solve_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM);
         configured = true;
     }
-    k_pent_solve_tma<<<nBatch / 32, 64, TMA_SMEM>>>(tm, tabF, tabB, n, 0u);
+    k_pent_solve_tma<<<nBatch / 32, 64, TMA_SMEM>>>(tm, tabF, tabB, n);
     return true;
 }
 
