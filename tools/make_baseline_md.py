@@ -57,6 +57,18 @@ unregistered user function).
     L.append(f"| 2: 2d_x_p 9-pt, 8192^2, 1 GPU | {b['x_p_8192']['gpoints_per_s']:.1f} Gpt/s = {100 * b['x_p_8192']['frac_of_peak']:.1f} % of HBM peak (bit-identical to the reference kernel at this size, `tests/test_parity_gpu.py::test_reference_kernels_at_config2_size`) |")
     L.append(f"| 3: 2d_xy_np 3x3, 16384^2, numTiles = 4, device-resident | {b['xy_np_16384_t4']['gpoints_per_s']:.1f} Gpt/s = {100 * b['xy_np_16384_t4']['frac_of_peak']:.1f} % of HBM peak (tiles are contiguous: one launch) |")
     L.append(f"| 4: 2d_xy_p_fun (c^3 - c), 32768^2, 1 GPU | {b['value']:.1f} Gpt/s = {b['roofline']['achieved']:.0f} GB/s = {100 * b['roofline']['frac']:.1f} % of HBM peak; ncu DRAM traffic {b['roofline']['traffic'] / 1e9:.2f} GB per sweep vs 17.18 GB algorithmic |")
+    um = b.get("xy_np_16384_t4_unified_memory") or {}
+    if "default" in um:
+        d0, r0 = um["default"], um["reference_pipeline"]
+        L.append(f"| 3: same sweep on unified memory (`cudaMallocManaged`, what the reference requires), numTiles = 4, offload = DEVICE | "
+                 f"{d0['offload_DEVICE']['gpoints_per_s']:.0f} Gpt/s ({d0['offload_DEVICE']['ms_per_step']:.2f} ms; the grid is already on the GPU, "
+                 f"no prefetch is issued); the reference's prefetch pipeline on every call: {r0['offload_DEVICE']['gpoints_per_s']:.0f} Gpt/s "
+                 f"({r0['offload_DEVICE']['ms_per_step']:.2f} ms, the no-op prefetches cost more than the sweep) |")
+        L.append(f"| 3: same, offload = HOST (the grid lives on the CPU between sweeps) | "
+                 f"{d0['offload_HOST']['gpoints_per_s']:.2f} Gpt/s ({d0['offload_HOST']['ms_per_step']:.0f} ms; swept in place over the host link, "
+                 f"{d0['offload_HOST']['host_link_gbs_each_way']} GB/s each way: 8 B in + 8 B out per point); the reference's pipeline "
+                 f"(every tile migrated to the GPU and back, 16 B per point each way): {r0['offload_HOST']['gpoints_per_s']:.2f} Gpt/s "
+                 f"({r0['offload_HOST']['ms_per_step']:.0f} ms, {r0['offload_HOST']['host_link_gbs_each_way']} GB/s each way) |")
     for n, d in sorted(multi.items()):
         he = d.get("halo_exchange") or {}
         L.append(f"| 4: same grid on {n} GPUs (y-slabs, strong scaling, {d['config']['parallelism']}) | {d['value']:.0f} Gpt/s, {d['ms_per_step']:.3f} ms/sweep = {100 * d['value'] / (n * b['value']):.0f} % of ideal"
@@ -70,25 +82,28 @@ unregistered user function).
     L.append("""
 ### 5.3 Config 5: Cahn-Hilliard ADI (bit-identical to the reference's GPU solver)
 
-| n | reference GPU solver (sm_100 rebuild, managed memory, 13 syncs/step) | new engine, 1 GPU | speed-up | reference serial CPU (1 core) |
-|---|---|---|---|---|""")
+| n | reference GPU solver (sm_100 rebuild, managed memory, 13 syncs/step) | new engine, 1 GPU (fused right-hand side + TMA-fed solve) | speed-up | same step through the engine's public API (cuStenCompute2D*, cp.async solve) | reference serial CPU (1 core) |
+|---|---|---|---|---|---|""")
     for n in (512, 4096):
         r = ref.get(f"cahn_hilliard_{n}")
         o = ch.get(f"cahn_hilliard_{n}")
         if r and o:
             cpu = f"{c1['seconds'] / c1['steps'] * 1e3:.1f} ms/step" if n == 512 and c1.get("seconds") else "-"
-            L.append(f"| {n} | {r['ms_per_step']:.3f} ms/step | {o['ms_per_step']:.3f} ms/step ({o['mpoint_steps_per_s'] / 1e3:.2f} Gpoint-steps/s) | {r['ms_per_step'] / o['ms_per_step']:.0f}x | {cpu} |")
+            eng = f"{o['engine_path_ms_per_step']:.3f} ms/step" if "engine_path_ms_per_step" in o else "-"
+            L.append(f"| {n} | {r['ms_per_step']:.3f} ms/step | {o['ms_per_step']:.3f} ms/step ({o['mpoint_steps_per_s'] / 1e3:.2f} Gpoint-steps/s) | {r['ms_per_step'] / o['ms_per_step']:.0f}x | {eng} | {cpu} |")
     if os.path.exists(P("r1_cahn_slab_multi_gpu.jsonl")):
         L.append("\nMulti-GPU (y-slabs, peer halos, two all-to-all transposes per step; bit-identical to 1 GPU):\n\n| n | GPUs | ms/step |\n|---|---|---|")
         for ln in open(P("r1_cahn_slab_multi_gpu.jsonl")):
             d = json.loads(ln)
-            L.append(f"| {d['n']} | {d['gpus']} | {d['ms_per_step']:.3f} |")
-        L.append("\nThe bit-identical solve is a sequential recurrence per system (one thread each, ~0.24 ms at n = 4096 however few "
-                 "systems a GPU holds), so config 5 gains little from more GPUs; see DESIGN.md section 7.")
+            L.append(f"| {d['n']} | {d['gpus']} | {d['ms_per_step']:.3f} |" + (f" {d['note']}" if d.get("note") else ""))
+        L.append("\nThe bit-identical solve is a sequential recurrence per system (~0.15 ms at n = 4096 however few systems a GPU "
+                 "holds), so config 5 gains little from more GPUs; see DESIGN.md section 7.")
     L.append("""
-Step breakdown at 4096^2 on 1 GPU (ncu launch list, `profiles/r1_launches_cahn4096.csv`): two cyclic pentadiagonal solves
-2 x 243 us (issue-latency bound, 31 instructions per row), two stencils ~100 us, the three fused pointwise/transposes
-passes ~200 us, `findCBar` 61 us.
+Step breakdown at 4096^2 on 1 GPU (ncu launch list, `profiles/r1_launch_list_cahn4096.md`): right-hand side in one pass
+117 us (shared-memory bandwidth and FP64 bound; it reads c and cOld once, 269 MB, and writes rhs^T), two cyclic pentadiagonal
+solves 2 x 144 us (dependent-FP64-latency bound: 6 chained operations of 8 cycles per row and system, `profiles/r1_fp64_latency.log`,
+i.e. 103 us at best), rank-2 correction + transpose 55 us, correction + `findNew` 79 us (4 array passes, at the HBM roofline).
+The same step at the start of the round (separate cBar / stencil / rhs passes, cp.async solve): 0.92 ms.
 """)
     s = open(os.path.join(ROOT, "BASELINE.md")).read()
     if "\n## 5. Measured on B200" in s:
