@@ -92,10 +92,10 @@ unregistered user function).
             eng = f"{o['engine_path_ms_per_step']:.3f} ms/step" if "engine_path_ms_per_step" in o else "-"
             L.append(f"| {n} | {r['ms_per_step']:.3f} ms/step | {o['ms_per_step']:.3f} ms/step ({o['mpoint_steps_per_s'] / 1e3:.2f} Gpoint-steps/s) | {r['ms_per_step'] / o['ms_per_step']:.0f}x | {eng} | {cpu} |")
     if os.path.exists(P("r1_cahn_slab_multi_gpu.jsonl")):
-        L.append("\nMulti-GPU (y-slabs, peer halos, two all-to-all transposes per step; bit-identical to 1 GPU):\n\n| n | GPUs | ms/step |\n|---|---|---|")
+        L.append("\nMulti-GPU (y-slabs, peer halos, two all-to-all transposes per step; bit-identical to 1 GPU):\n\n| n | GPUs | ms/step | |\n|---|---|---|---|")
         for ln in open(P("r1_cahn_slab_multi_gpu.jsonl")):
             d = json.loads(ln)
-            L.append(f"| {d['n']} | {d['gpus']} | {d['ms_per_step']:.3f} |" + (f" {d['note']}" if d.get("note") else ""))
+            L.append(f"| {d['n']} | {d['gpus']} | {d['ms_per_step']:.3f} | {d.get('note', '')} |")
         L.append("\nThe bit-identical solve is a sequential recurrence per system (~0.15 ms at n = 4096 however few systems a GPU "
                  "holds), so config 5 gains little from more GPUs; see DESIGN.md section 7.")
     L.append("""
