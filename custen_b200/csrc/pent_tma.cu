@@ -449,11 +449,14 @@ bool pent_tma_solve(double* data, int nBatch, int n, const double* tabF, const d
 {
     CUtensorMap tm;
     if (!make_rhs_map(&tm, data, nBatch, n)) return false;
-    static bool configured = false;
-    if (!configured)
+    // the opt-in to more than 48 KB of dynamic shared memory is per device
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev])
     {
         cudaFuncSetAttribute(k_pent_solve_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM);
-        configured = true;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     k_pent_solve_tma<<<nBatch / 32, 64, TMA_SMEM>>>(tm, tabF, tabB, n);
     return true;
