@@ -39,7 +39,7 @@ EXPORTED = (
        "custen_event_synchronize", "custen_event_elapsed_ms", "custen_event_destroy", "custen_host_alloc",
        "custen_host_free", "custen_managed_alloc", "custen_managed_free", "custen_peer_barrier", "custen_device_alloc",
        "custen_device_free", "custen_cahn_create", "custen_cahn_set_field", "custen_cahn_step", "custen_cahn_get_field",
-       "custen_cahn_time_steps", "custen_cahn_destroy", "custen_cahn_set_table_rows", "custen_cahn_set_solver", "custen_cahn_set_fused", "custen_debug_bands", "custen_cahn_slab_create",
+       "custen_cahn_time_steps", "custen_cahn_destroy", "custen_cahn_set_table_rows", "custen_cahn_set_solver", "custen_cahn_set_fused", "custen_cahn_set_graph", "custen_debug_bands", "custen_cahn_slab_create",
        "custen_cahn_slab_buffer", "custen_cahn_slab_handle", "custen_cahn_slab_current", "custen_cahn_slab_phase",
        "custen_cahn_slab_set_field", "custen_cahn_slab_get_field"]
 )
@@ -105,6 +105,7 @@ def load():
     lib.custen_cahn_set_table_rows.argtypes, lib.custen_cahn_set_table_rows.restype = [_c_int], None
     lib.custen_cahn_set_solver.argtypes, lib.custen_cahn_set_solver.restype = [_c_int], None
     lib.custen_cahn_set_fused.argtypes, lib.custen_cahn_set_fused.restype = [_c_int], None
+    lib.custen_cahn_set_graph.argtypes, lib.custen_cahn_set_graph.restype = [_c_int], None
     lib.custen_cahn_slab_create.argtypes = [_c_int, _c_int, _c_int] + [ctypes.c_double] * 4 + [_c_int]
     lib.custen_cahn_slab_create.restype = ctypes.c_void_p
     lib.custen_cahn_slab_buffer.argtypes, lib.custen_cahn_slab_buffer.restype = [_c_void_p, _c_int], ctypes.c_void_p

@@ -445,7 +445,7 @@ void pent_tma_build_tables(const double* ds, const double* dl, const double* d, 
     k_build_tables<<<(trows + 127) / 128, 128>>>(ds, dl, d, du, dw, rinv, tabF, tabB, m, trows);
 }
 
-bool pent_tma_solve(double* data, int nBatch, int n, const double* tabF, const double* tabB)
+bool pent_tma_solve(double* data, int nBatch, int n, const double* tabF, const double* tabB, cudaStream_t stream)
 {
     CUtensorMap tm;
     if (!make_rhs_map(&tm, data, nBatch, n)) return false;
@@ -458,7 +458,7 @@ bool pent_tma_solve(double* data, int nBatch, int n, const double* tabF, const d
         cudaFuncSetAttribute(k_pent_solve_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM);
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
-    k_pent_solve_tma<<<nBatch / 32, 64, TMA_SMEM>>>(tm, tabF, tabB, n);
+    k_pent_solve_tma<<<nBatch / 32, 64, TMA_SMEM, stream>>>(tm, tabF, tabB, n);
     return true;
 }
 

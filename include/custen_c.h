@@ -152,6 +152,7 @@ void custen_cahn_get_field(void* solver, double* out_host);     /* synchronises 
 float custen_cahn_time_steps(void* solver, int nsteps);         /* milliseconds for nsteps steps (CUDA events) */
 void custen_cahn_destroy(void* solver);
 void custen_cahn_set_fused(int on);                             /* 1: fused right-hand-side pass (default), 0: via cuStenCompute2D* */
+void custen_cahn_set_graph(int on);                             /* 1: replay the fused step from a CUDA graph (default), 0: kernel by kernel */
 void custen_cahn_set_solver(int which);                         /* 0: TMA-fed pentadiagonal solve (default), 1: cp.async ring version */
 void custen_cahn_set_table_rows(int rows);                      /* tuning / tests: coefficient rows staged per refill */
 

@@ -138,3 +138,31 @@ def test_fused_right_hand_side_matches_the_engine_path(n):
     b = _ours(c0, 5, fused=0)
     assert np.isfinite(a).all()
     assert ol.count_diff(a, b) == 0
+
+
+@pytest.mark.parametrize("n,steps", [(128, 1), (128, 2), (256, 7), (512, 12)])
+def test_graph_replay_matches_kernel_by_kernel(n, steps):
+    """The fused step replayed from a CUDA graph (pairs of steps; the first step and an odd last one run kernel by
+    kernel) against plain launches, also when steps are requested in several calls."""
+    import custen_b200 as cs
+    c0 = _initial(n, seed=3 * n + steps)
+    cs.load().custen_cahn_set_graph(0)
+    try:
+        want = _ours(c0, steps)
+    finally:
+        cs.load().custen_cahn_set_graph(1)
+    got = _ours(c0, steps)
+    assert ol.count_diff(got, want) == 0
+    s = CahnHilliard(n, lx=LX)
+    s.set_field(c0)
+    done = 0
+    for chunk in (1, 3, 2, 5, 1):
+        k = min(chunk, steps - done)
+        if k > 0:
+            s.step(k)
+            done += k
+    if done < steps:
+        s.step(steps - done)
+    split = s.field()
+    s.destroy()
+    assert ol.count_diff(split, want) == 0
