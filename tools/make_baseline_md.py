@@ -22,7 +22,9 @@ def main():
 All numbers: B200 (148 SMs, SM clock 1965 MHz during the runs, no throttle reasons), FP64, grids device-resident unless
 stated, CUDA-event timing (3 warm-ups, 10-20 timed sweeps, inputs far larger than L2). Roofline denominator: the driver's
 measured copy bandwidth 6548.5 GB/s (`MEASURED_PEAKS.json`); algorithmic traffic 16 B/point (WENO: 32). Raw lines:
-`profiles/r1_*.json`; regenerate this section with `python tools/make_baseline_md.py`.
+`profiles/r1_*.json`; regenerate this section with `python tools/make_baseline_md.py`. Every `gpurun` call lands on a
+different B200: over this round's runs the headline value (config 4, one GPU) came out at 362, 366, 371, 376, 378, 381
+and 406 Gpt/s (the power-capped boxes at both ends of that range); the table below is from the last run.
 
 ### 5.1 Every variant on 16384^2 (target: >= 80 % of HBM peak) - new engine vs the reference's own kernels on the same GPU
 
