@@ -19,7 +19,8 @@ def main():
     L.append("""
 ## 5. Measured on B200 (round 1)
 
-All numbers: B200 (148 SMs, SM clock 1965 MHz during the runs, no throttle reasons), FP64, grids device-resident unless
+All numbers: B200 (148 SMs; SM clock sampled under load between 1575 and 1965 MHz, `sw_power_cap` reported on some boxes
+and kept in the bench line's `clocks`, no thermal or hardware slow-down), FP64, grids device-resident unless
 stated, CUDA-event timing (3 warm-ups, 10-20 timed sweeps, inputs far larger than L2). Roofline denominator: the driver's
 measured copy bandwidth 6548.5 GB/s (`MEASURED_PEAKS.json`); algorithmic traffic 16 B/point (WENO: 32). Raw lines:
 `profiles/r1_*.json`; regenerate this section with `python tools/make_baseline_md.py`. Every `gpurun` call lands on a
