@@ -18,11 +18,11 @@ namespace custen_cahn {
 // ---- the same solve fed by the TMA engine -----------------------------------------------------------------------------
 // A warp that is alone on its scheduler issues in order, so every instruction that is not one of the recurrence's
 // dependent FP64 operations (8 cycles each, tools/fp64_latency.cu: 4 per row forward, 2 backward) has to fit in the gaps
-// between them.  The cp.async version above spends ~17 instructions per row (per-lane 64-bit address arithmetic for every
-// LDGSTS and STG) and runs at ~57 cycles per row and direction.  Here a CTA is two warps on two schedulers:
-//   * the math warp touches shared memory only: per group of TG rows it waits for the group's slot, pulls right-hand
-//     sides and coefficients into registers (one group ahead of the arithmetic), runs the chain, writes the results back
-//     into the slot and arrives on the slot's `done` barrier.  Per row: LDS rhs, 2 x LDS.128 coefficients, the chain, STS;
+// between them.  The cp.async version (k_pent_solve_smem, cahn.cu) spends ~17 instructions per row (per-lane 64-bit address
+// arithmetic for every LDGSTS and STG) and runs at ~57 cycles per row and direction.  Here a CTA is two warps on two schedulers:
+//   * the math warp touches shared memory only: per group of TG rows it waits for the group's slot, keeps a rolling
+//     window of TW rows (right-hand sides and coefficients) in registers, runs the chain, writes the results back into
+//     the slot and arrives on the slot's `done` barrier.  Per row: LDS rhs, 2 x LDS.128 coefficients, the chain, STS;
 //   * one lane of the copy warp moves everything through the async proxy: one 2-D tensor copy brings TG rows x 32
 //     systems into a slot, one 1-D bulk copy brings the group's coefficients (a table pre-interleaved at factor time),
 //     one tensor store takes the results back.  Loads run TAHEAD groups ahead; a slot is refilled once its store has
