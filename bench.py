@@ -6,9 +6,11 @@
 Default workload (every N): BASELINE.json configs[3], the 2D XY periodic function-pointer stencil (nonlinear
 c^3 - c term through a 3x3 Laplacian, cuPentCahnADI.cu:164-188) on a 32768^2 FP64 grid — the configuration the
 multi-GPU target is quoted on; it fits one B200 (2 x 8 GiB), so N = 1 runs the same grid and the scaling is strong.
-A step is one sweep of the whole grid: at N > 1 each rank owns a y-slab and a step is halo transport + sweep.
-At N = 1 the line also carries a per-variant table on 16384^2 (the single-GPU target size) and the configs[1] /
-configs[2] workloads.
+A step is one TIME STEP of the whole grid: Compute + Swap (the output of a step is the input of the next), so at N > 1
+every sweep depends on the neighbours' previous one and the halo rows it reads over NVLink are fresh every step.
+After the timed loop every rank checks the rows either side of its seams against the oracle (`parity` key; a
+mismatch fails the run).  At N = 1 the line also carries a per-variant table on 16384^2 (the single-GPU target size)
+and the configs[1] / configs[2] workloads.
 
 `value` is timed with inputs resident in HBM; `e2e` goes through the same C ABI with the grid in pinned HOST
 memory (the numTiles out-of-core path: H2D of every tile and D2H of every result inside the timed region).
@@ -44,30 +46,102 @@ WORKLOADS = {
 }
 
 
-def stencil_args(variant, n):
+SEED = 0x5EED
+
+
+def _w_d2_8th(h):
+    """9-point 8th-order second derivative (examples/src/2d_x_p.cu:99-114)."""
+    return np.array([-1.0 / 560, 8.0 / 315, -1.0 / 5, 8.0 / 5, -205.0 / 72, 8.0 / 5, -1.0 / 5, 8.0 / 315, -1.0 / 560]) / (h * h)
+
+
+def _w_cross_xy(dx, dy):
+    """3x3 cross derivative d2/dxdy (examples/src/2d_xy_p.cu:112-120)."""
+    s = 1.0 / (4.0 * dx * dy)
+    return np.array([s, 0.0, -s, 0.0, 0.0, 0.0, -s, 0.0, s])
+
+
+def _w_laplace5(sig):
+    """3x3 five-point Laplacian times sigma (cuPentCahnADI.cu:511-513)."""
+    return np.array([0, 1, 0, 1, -4, 1, 0, 1, 0], dtype=np.float64) * sig
+
+
+def stencil_args(variant, n, time_stepping=False):
     """Coefficients / window of the named workloads (SURVEY.md section 8d 'synthetic inputs')."""
-    import cases
     h = 2 * np.pi / n
     d = "XY" if variant.startswith("XY") else variant[0]
     fun = None
     if d == "X":
-        coef, kw = cases.weights_d2_8th(h), dict(H=9, L=4, R=4)
+        coef, kw = _w_d2_8th(h), dict(H=9, L=4, R=4)
         if variant.endswith("Fun"):
             fun, kw["numCoe"] = "weighted9_x", 9
     elif d == "Y":
-        coef, kw = cases.weights_d2_8th(h), dict(V=9, T=4, B=4)
+        coef, kw = _w_d2_8th(h), dict(V=9, T=4, B=4)
         if variant.endswith("Fun"):
             fun = "weighted9_y"
             if variant == "YpFun":
                 kw["numCoe"] = 9
     elif variant.endswith("Fun"):
-        # sigma_N * 5-point Laplacian applied to c^3 - c (cuPentCahnADI.cu:496-516), dt = 0.1 dx, D = 1
-        dx = 16 * np.pi / n
-        coef, kw, fun = cases.weights_laplace5((0.1 * dx / 3.0) * 2.0 / dx ** 2), dict(H=3, L=1, R=1, V=3, T=1, B=1), "cubic_xy"
+        kw, fun = dict(H=3, L=1, R=1, V=3, T=1, B=1), "cubic_xy"
+        if time_stepping:
+            # the same user function (sum of coe * (c^3 - c) over the 3x3 window) with coefficients that make the
+            # map c -> f(c) a bounded iteration: c' = h + eps Lap5(h), h = c - c^3 (an explicit Allen-Cahn-like step).
+            # With the solver's own sigma_N (~43 at this size) the bare stencil is not a time stepper: it overflows
+            # within a few applications.  Arithmetic per point is identical.
+            eps = 0.05
+            coef = np.array([0, -eps, 0, -eps, -1 + 4 * eps, -eps, 0, -eps, 0], dtype=np.float64)
+        else:
+            # sigma_N * 5-point Laplacian applied to c^3 - c (cuPentCahnADI.cu:496-516), dt = 0.1 dx, D = 1
+            dx = 16 * np.pi / n
+            coef = _w_laplace5((0.1 * dx / 3.0) * 2.0 / dx ** 2)
     else:
-        coef, kw = cases.weights_cross_xy(h, h), dict(H=3, L=1, R=1, V=3, T=1, B=1)
+        coef, kw = _w_cross_xy(h, h), dict(H=3, L=1, R=1, V=3, T=1, B=1)
+        if time_stepping:
+            coef = coef / np.abs(coef).sum()
     kw["fun"] = fun
-    return coef, kw
+    return np.ascontiguousarray(coef, dtype=np.float64), kw
+
+
+def hash_rows(row0, rows, nx, seed, lo, hi):
+    """numpy twin of custen_fill_hash (custen_b200/csrc/api_c.cu): rows [row0, row0 + rows) of the synthetic field."""
+    idx = (np.uint64(row0) * np.uint64(nx) + np.arange(rows * nx, dtype=np.uint64))
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed) + idx * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    u = (z >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+    return (lo + (hi - lo) * u).reshape(rows, nx)
+
+
+def seam_parity(variant, coef, kw, n, total_steps, row_lo, row_hi, final_rows_of, margin=2):
+    """Checker (the oracle, oracle/custen_oracle.c - never on the timed path): after `total_steps` time steps, the
+    `margin` rows either side of each end of this rank's slab [row_lo, row_hi) must equal what the oracle gets by
+    time-stepping just the band of the GLOBAL initial field those rows depend on (x wraps, the band shrinks by T + B
+    rows per step).  final_rows_of(global_row_list) returns this rank's final values of those rows.
+    Returns (rows checked, doubles differing)."""
+    import oracle_lib as ol
+    T, B = kw.get("T", 0), kw.get("B", 0)
+    fun = kw.get("fun")
+    okw = {k: v for k, v in kw.items() if k in ("H", "L", "R", "V")}
+    checked = differing = 0
+    targets = [(row_lo, min(row_lo + margin, row_hi)), (max(row_hi - margin, row_lo), row_hi)]
+    for g0, g1 in targets:
+        b0, b1 = g0 - total_steps * T, g1 + total_steps * B
+        rows = [(r % n) for r in range(b0, b1)]
+        # contiguous runs of the wrapped row list, regenerated from the counter-based hash
+        parts, start = [], 0
+        for i in range(1, len(rows) + 1):
+            if i == len(rows) or rows[i] != rows[i - 1] + 1:
+                parts.append(hash_rows(rows[start], i - start, n, SEED, -0.1, 0.1))
+                start = i
+        band = np.ascontiguousarray(np.vstack(parts))
+        got_band, v0, v1 = ol.oracle_evolve_band(variant, band, coef, total_steps, T, B, fun=fun, **okw)
+        want = got_band[v0:v1]
+        assert want.shape[0] == g1 - g0
+        got = final_rows_of(list(range(g0, g1)))
+        differing += ol.count_diff(got, want)
+        checked += g1 - g0
+    return checked, differing
 
 
 class ClockSampler:
@@ -127,9 +201,8 @@ def cpu_sweeps(n, threads, repeats):
     nonlinearRHS (serialCahnADI.c:553-622).  Returns seconds for the whole batch."""
     lib = _serial_lib()
     _dp = ctypes.POINTER(ctypes.c_double)
-    import cases
     dx = 16 * np.pi / n
-    w = np.ascontiguousarray(cases.weights_laplace5((0.1 * dx / 3.0) * 2.0 / dx ** 2))
+    w = np.ascontiguousarray(_w_laplace5((0.1 * dx / 3.0) * 2.0 / dx ** 2))
     rng = np.random.default_rng(1)
     bufs = [(np.ascontiguousarray(rng.uniform(-0.1, 0.1, (n, n))), np.zeros((n, n))) for _ in range(threads)]
 
@@ -161,8 +234,12 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "description": desc,
-                   "note": "reference CPU implementation of the path: serialCahnADI.c nonlinearRHS (3x3 c^3-c stencil, periodic)"},
+        "config": {"workload": "xy_p_fun_%d_per_core" % n, "sample_of": args.workload, "description": desc,
+                   "same_config_as_gpu_arm": False,
+                   "note": "reference CPU implementation of the path: serialCahnADI.c nonlinearRHS (3x3 c^3-c stencil, periodic); "
+                           "each host thread sweeps its own %d^2 periodic field (that function only takes square grids and is "
+                           "serial), a bounded and cache-friendlier sample of the 32768^2 workload, so the ratio against it is "
+                           "conservative; the reference's CUDA library on the same B200 is in profiles/r1_reference_gpu_16384.json" % n},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
                          "sample": f"{cores} threads x {args.steps} sweeps of an independent {n}^2 periodic field each"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -264,89 +341,135 @@ def run_ours(args, rank, world, local_rank):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     variant, n, tiles, desc = WORKLOADS[args.workload]
-    coef, kw = stencil_args(variant, n)
+    coef_ts, kw = stencil_args(variant, n, time_stepping=True)
+    coef, _ = stencil_args(variant, n)
     rows = n // world
     peak, peak_src = peaks()
+    lib = cs.load()
+    tcoef = torch.from_numpy(coef).cuda()
+    T, B = (0, 0) if variant[0] == "X" and not variant.startswith("XY") else (kw.get("T", 0), kw.get("B", 0))
 
-    gen = torch.Generator(device="cuda").manual_seed(0x5EED + rank)
-    inp = torch.rand((rows, n), generator=gen, device="cuda", dtype=torch.float64) * 0.2 - 0.1
-    out = torch.zeros_like(inp)
-    tcoef = torch.from_numpy(np.ascontiguousarray(coef)).cuda()
-
-    # ---- resident timing ----------------------------------------------------------------------------------
-    sampler = ClockSampler(local_rank)
-    if world == 1:
-        st = cs.Stencil2D(variant, n, n, out, inp, tcoef, numTiles=tiles, deviceNum=local_rank, **kw)
-        ms = time_resident(cs, st, args.steps, args.warmup)
-        path = st.path
-        launches_timed = time_resident.launches
-        st.destroy()
-    else:
-        ss = slab.SlabStencil(variant, n, n, inp, out, tcoef, transport=args.transport, numTiles=tiles, **kw)
-        for _ in range(args.warmup):
-            ss.step()
-        torch.cuda.synchronize()
+    # ---- resident timing: K time steps (Compute + Swap) through the C slab layer -----------------------------------
+    # world == 1 is the same code with a single slab whose halo rows are its own far edge (plain periodic wrap).
+    ss = slab.SlabStencil(variant, n, n, coef_ts, transport=args.transport, numTiles=tiles, **kw)
+    lib.custen_fill_hash(ss.input.data_ptr(), ss.row0, rows, n, SEED, -0.1, 0.1)
+    torch.cuda.synchronize()
+    if dist:
         dist.barrier()
-        torch.cuda.synchronize()
+    ss.run(args.warmup)
+    ss.synchronize()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    l0 = cs.launch_count()
+    if ss.slab:
+        ms = float(lib.custen_slab_time_run(ss.slab, args.steps))     # events on the slab's stream, synchronises
+    else:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = cs.launch_count()
         e0.record()
-        for _ in range(args.steps):
-            ss.step()
+        ss.run(args.steps)
         e1.record()
         torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+    launches_timed = cs.launch_count() - l0
+    clocks = sampler.stop()
+    if dist:
         dist.barrier()
-        launches_timed = cs.launch_count() - l0
-        t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-        path = ss.st.path
-        # halo traffic: (T + B) rows of nx doubles per GPU per sweep; timed on its own as an NCCL exchange
-        T, B = kw.get("T", 0), kw.get("B", 0)
-        halo = None
-        if T + B:
-            periodic = not variant.replace("Fun", "").endswith("np")
-            top = torch.empty((max(T, 1), n), device="cuda", dtype=torch.float64)
-            bot = torch.empty((max(B, 1), n), device="cuda", dtype=torch.float64)
-            for _ in range(3):
-                slab.exchange_halos(inp, T, B, top[:T], bot[:B], rank, world, periodic)
-            torch.cuda.synchronize()
-            dist.barrier()
-            h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            h0.record()
-            for _ in range(20):
-                slab.exchange_halos(inp, T, B, top[:T], bot[:B], rank, world, periodic)
-            h1.record()
-            torch.cuda.synchronize()
-            th = torch.tensor([h0.elapsed_time(h1) / 20], device="cuda", dtype=torch.float64)
-            dist.all_reduce(th, op=dist.ReduceOp.MAX)
-            hb = (T + B) * n * 8
-            halo = {"bytes_received_per_gpu_per_sweep": hb, "transport_in_timed_region": args.transport,
-                    "nccl_exchange_us": round(float(th.item()) * 1e3, 1),
-                    "nccl_exchange_nvlink_gbs_per_gpu": round(hb / (float(th.item()) * 1e-3) / 1e9, 2),
-                    "in_sweep_gbs_per_gpu": round(hb / (ms / args.steps * 1e-3) / 1e9, 2),
-                    "note": "peer transport: the sweep's TMA producer reads the rows from the neighbours' memory, no separate "
-                            "exchange; the NCCL figure is the same rows sent with send/recv on their own (latency-bound)"}
-        ss.destroy()
-    if world == 1:
-        halo = None
-    clocks = sampler.stop()
+    path = ss.path
+    timed_out = ss.error()
+
+    # ---- parity: the rows either side of this rank's seams (and one interior row) against the oracle ---------------
+    parity = None
+    if not args.no_parity:
+        total = args.warmup + args.steps
+        final = ss.input
+
+        def final_rows_of(global_rows):
+            idx = torch.tensor([r - ss.row0 for r in global_rows], device="cuda")
+            return final.index_select(0, idx).cpu().numpy()
+
+        t0p = time.perf_counter()
+        checked, differing = seam_parity(variant, coef_ts, kw, n, total, ss.row0, ss.row0 + rows, final_rows_of)
+        mid = ss.row0 + rows // 2
+        c2, d2 = seam_parity(variant, coef_ts, kw, n, total, mid, mid + 1, final_rows_of, margin=1)
+        checked, differing = checked + c2 // 2, differing + d2 // 2   # the one-row target is visited as both of its ends
+        pv = torch.tensor([checked, differing, int(timed_out)], device="cuda", dtype=torch.int64)
+        if dist:
+            dist.all_reduce(pv)
+        parity = {"rows_checked": int(pv[0]), "bits_differing": int(pv[1]), "neighbour_wait_timeouts": int(pv[2]),
+                  "time_steps_compared": total, "checker_seconds": round(time.perf_counter() - t0p, 1),
+                  "what": "final rows next to every slab seam (2 either side) and one interior row per rank, against "
+                          "oracle/custen_oracle.c time-stepping the band of the regenerated global initial field they "
+                          "depend on; doubles compared bit for bit"}
+
+    # halo traffic: (T + B) rows of nx doubles per GPU per sweep; the same rows timed on their own as an NCCL exchange
+    halo = None
+    if world > 1 and T + B:
+        periodic = not variant.replace("Fun", "").endswith("np")
+        top = torch.empty((max(T, 1), n), device="cuda", dtype=torch.float64)
+        bot = torch.empty((max(B, 1), n), device="cuda", dtype=torch.float64)
+        inp = ss.input
+        for _ in range(3):
+            slab.exchange_halos(inp, T, B, top[:T], bot[:B], rank, world, periodic)
+        torch.cuda.synchronize()
+        dist.barrier()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record()
+        for _ in range(20):
+            slab.exchange_halos(inp, T, B, top[:T], bot[:B], rank, world, periodic)
+        h1.record()
+        torch.cuda.synchronize()
+        th = torch.tensor([h0.elapsed_time(h1) / 20], device="cuda", dtype=torch.float64)
+        dist.all_reduce(th, op=dist.ReduceOp.MAX)
+        hb = (T + B) * n * 8
+        halo = {"bytes_received_per_gpu_per_sweep": hb, "transport_in_timed_region": args.transport,
+                "nccl_exchange_us": round(float(th.item()) * 1e3, 1),
+                "nccl_exchange_nvlink_gbs_per_gpu": round(hb / (float(th.item()) * 1e-3) / 1e9, 2),
+                "in_sweep_gbs_per_gpu": round(hb / (ms / args.steps * 1e-3) / 1e9, 2),
+                "note": "peer transport: the sweep's TMA producer reads the rows from the neighbours' memory and waits for "
+                        "the neighbour inside the kernel, in front of the halo rows only - no exchange step, no barrier "
+                        "kernel; the NCCL figure is the same rows sent with send/recv on their own (latency-bound)"}
+        del top, bot
+    ss.destroy()
     ms_per_step = ms / args.steps
     value = n * n / ms_per_step / 1e6  # Gpoints/s, whole job
 
     # ---- end to end: grid in pinned host memory, through the out-of-core tile scheduler -----------------------
     e2e = None
     if not args.no_e2e:
-        lib = cs.load()
         nbytes = rows * n * 8
-        h_in, h_out = lib.custen_host_alloc(nbytes), lib.custen_host_alloc(nbytes)
+        node = ctypes.c_int(-1)
+        h_in = lib.custen_host_alloc_near(nbytes, local_rank, ctypes.byref(node))
+        h_out = lib.custen_host_alloc_near(nbytes, local_rank, None)
+        near = bool(h_in and h_out)
+        if not near:   # mmap / registration refused: ordinary pinned memory
+            h_in, h_out = lib.custen_host_alloc(nbytes), lib.custen_host_alloc(nbytes)
         v_in = np.ctypeslib.as_array((ctypes.c_double * (rows * n)).from_address(h_in))
-        torch.from_numpy(v_in).copy_(inp.view(-1).cpu())
+        tmp = torch.empty((rows, n), device="cuda", dtype=torch.float64)
+        lib.custen_fill_hash(tmp.data_ptr(), rank * rows, rows, n, SEED, -0.1, 0.1)
+        torch.from_numpy(v_in).copy_(tmp.view(-1))
+        torch.cuda.synchronize()
+        del tmp
+        torch.cuda.empty_cache()
+        # what the host link carries with plain copies both ways at once, all ranks at the same time
+        if dist:
+            dist.barrier()
+        lib.custen_link_probe(h_in, h_out, nbytes, 1, local_rank)
+        if dist:
+            dist.barrier()
+        probe_ms = float(lib.custen_link_probe(h_in, h_out, nbytes, 2, local_rank)) / 2
+        tp = torch.tensor([probe_ms], device="cuda", dtype=torch.float64)
+        if dist:
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        probe_ms = float(tp.item())
         e2e_tiles = max(tiles, args.e2e_tiles)
         st = cs.Stencil2D(variant, n, rows, h_out, h_in, tcoef, numTiles=e2e_tiles, deviceNum=local_rank, **kw)
         halo_bytes = 0
-        if world > 1 and not variant.startswith("Xp") and not variant.startswith("Xnp"):
-            T, B = kw.get("T", 0), kw.get("B", 0)
+        if world > 1 and T + B:
             top = torch.empty((max(T, 1), n), device="cuda", dtype=torch.float64)
             bot = torch.empty((max(B, 1), n), device="cuda", dtype=torch.float64)
             periodic = not variant.replace("Fun", "").endswith("np")
@@ -386,13 +509,32 @@ def run_ours(args, rank, world, local_rank):
         if dist:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_ms = float(tt.item()) / k
+        nodes = [None] * world
+        info = {"gpu_numa_node": int(lib.custen_device_numa_node(local_rank)), "buffers_bound_to_node": int(node.value),
+                "cpus": sorted(os.sched_getaffinity(0))[:: max(1, len(os.sched_getaffinity(0)) // 4)][:4]}
+        if dist:
+            dist.all_gather_object(nodes, info)
+        else:
+            nodes = [info]
+        ceiling_gbs = world * 2 * nbytes / (probe_ms * 1e-3) / 1e9      # both directions, all ranks
+        moved_gbs = world * (2 * nbytes + halo_bytes) / (e2e_ms * 1e-3) / 1e9
         e2e = {"value": n * n / e2e_ms / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(world * (nbytes + halo_bytes)),
                "d2h_bytes_per_step": int(world * nbytes), "ms_per_step": e2e_ms, "steps": k, "numTiles": e2e_tiles,
+               "host_link_gbs": round(moved_gbs, 1), "host_link_ceiling_gbs": round(ceiling_gbs, 1),
+               "link_frac": round(moved_gbs / ceiling_gbs, 3),
+               "ceiling_how": "custen_link_probe: cudaMemcpyAsync H2D and D2H of the same pinned buffers at once, every rank at "
+                              "the same time, max over ranks",
+               "host_buffers": "mmap + mbind to the GPU's NUMA node + cudaHostRegister" if near else "cudaHostAlloc",
+               "ranks": nodes,
                "path": "custenCompute2D%s(HOST) on pinned host buffers: staged tile pipeline" % variant}
         st.destroy()
         cs.device_synchronize()
-        lib.custen_host_free(h_in)
-        lib.custen_host_free(h_out)
+        if near:
+            lib.custen_host_free_near(h_in, nbytes)
+            lib.custen_host_free_near(h_out, nbytes)
+        else:
+            lib.custen_host_free(h_in)
+            lib.custen_host_free(h_out)
 
     if rank != 0:
         if dist:
@@ -400,7 +542,6 @@ def run_ours(args, rank, world, local_rank):
         return
 
     # ---- rank 0 extras: per-variant table, other configs, cpu baseline -----------------------------------------
-    del inp, out
     torch.cuda.empty_cache()
     extras = {}
     if world == 1 and not args.no_table:
@@ -521,24 +662,27 @@ def run_ours(args, rank, world, local_rank):
             except Exception as ex:
                 extras["config1_serial_cpu_cahn_512"] = {"error": str(ex)}
 
-    traffic = None
+    traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get(args.workload if world == 1 else "", None)
+        traffic_src = "stored_from_profiles (ncu --set full capture of this kernel, profiles/r1_ncu_full_summary.md); not measured in this run"
     achieved = value / world * ALG_BYTES_PER_POINT  # GB/s per GPU
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": args.workload, "description": desc, "grid": [n, n], "rows_per_gpu": rows,
-                   "numTiles": tiles, "parallelism": f"y-slabs x{world}" + (f", halo transport: {args.transport}" if world > 1 else ""),
+                   "numTiles": tiles, "step": "one time step = cuSten Compute + Swap on every slab (custen_slab_run)",
+                   "parallelism": f"y-slabs x{world}" + (f", halo transport: {args.transport}" if world > 1 else ""),
                    "l2": "no flush: every sweep streams 2 x %.1f GiB per GPU, far larger than the 126 MB L2" % (rows * n * 8 / 2 ** 30),
                    "kernel_family": path},
         "clocks": clocks,
         "e2e": e2e,
         "gpu_launches": int(launches_timed),
+        "parity": parity,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src,
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "note": "algorithmic 16 B/point x points per launch / mean launch duration (CUDA events on the "
                              "launching stream over the timed region); per GPU"},
         "cpu_baseline": cpu,
@@ -549,6 +693,9 @@ def run_ours(args, rank, world, local_rank):
     print(json.dumps(line))
     if dist:
         dist.destroy_process_group()
+    if parity and (parity["bits_differing"] or parity["neighbour_wait_timeouts"]):
+        sys.stderr.write("PARITY FAILURE: %s\n" % json.dumps(parity))
+        sys.exit(1)
 
 
 def main():
@@ -564,6 +711,7 @@ def main():
     ap.add_argument("--e2e-tiles", type=int, default=32)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the seam rows after the timed loop")
     ap.add_argument("--no-table", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-serial", action="store_true", help="skip the ~30 s serial CPU Cahn-Hilliard baseline (config 1)")

@@ -41,7 +41,14 @@ EXPORTED = (
        "custen_device_free", "custen_cahn_create", "custen_cahn_set_field", "custen_cahn_step", "custen_cahn_get_field",
        "custen_cahn_time_steps", "custen_cahn_destroy", "custen_cahn_set_table_rows", "custen_cahn_set_solver", "custen_cahn_set_fused", "custen_cahn_set_graph", "custen_debug_bands", "custen_cahn_slab_create",
        "custen_cahn_slab_buffer", "custen_cahn_slab_handle", "custen_cahn_slab_current", "custen_cahn_slab_phase",
-       "custen_cahn_slab_set_field", "custen_cahn_slab_get_field"]
+       "custen_cahn_slab_set_field", "custen_cahn_slab_get_field",
+       "custen_set_handle_managed_policy", "custen_mem_advise", "custen_mem_prefetch", "custen_fill_hash",
+       "custen_slab_create", "custen_slab_export", "custen_slab_connect", "custen_slab_field", "custen_slab_rows",
+       "custen_slab_compute", "custen_slab_swap", "custen_slab_run", "custen_slab_run_plain", "custen_slab_time_run",
+       "custen_slab_synchronize", "custen_slab_error", "custen_slab_set_timeout", "custen_slab_last_path",
+       "custen_slab_destroy", "custen_mg_create", "custen_mg_scatter", "custen_mg_gather", "custen_mg_fill_output",
+       "custen_mg_compute", "custen_mg_swap", "custen_mg_run", "custen_mg_synchronize", "custen_mg_error", "custen_mg_slab",
+       "custen_mg_destroy", "custen_device_numa_node", "custen_host_alloc_near", "custen_host_free_near", "custen_link_probe"]
 )
 
 _lib = None
@@ -118,6 +125,43 @@ def load():
     lib.custen_debug_bands.restype = _c_int
     lib.custen_managed_alloc.argtypes, lib.custen_managed_alloc.restype = [ctypes.c_size_t], ctypes.c_void_p
     lib.custen_managed_free.argtypes, lib.custen_managed_free.restype = [_c_void_p], None
+    lib.custen_set_handle_managed_policy.argtypes, lib.custen_set_handle_managed_policy.restype = [_c_void_p, _c_int], None
+    lib.custen_mem_advise.argtypes, lib.custen_mem_advise.restype = [_c_void_p, ctypes.c_size_t, _c_int, _c_int], _c_int
+    lib.custen_mem_prefetch.argtypes, lib.custen_mem_prefetch.restype = [_c_void_p, ctypes.c_size_t, _c_int], _c_int
+    lib.custen_fill_hash.argtypes = [_c_void_p, ctypes.c_longlong, _c_int, _c_int, ctypes.c_uint64, ctypes.c_double, ctypes.c_double]
+    lib.custen_fill_hash.restype = None
+    lib.custen_slab_create.argtypes = [_c_int] * 6 + [_c_void_p] + [_c_int] * 7 + [_c_void_p]
+    lib.custen_slab_create.restype = ctypes.c_void_p
+    lib.custen_slab_export.argtypes, lib.custen_slab_export.restype = [_c_void_p, _c_void_p, _c_void_p], None
+    lib.custen_slab_connect.argtypes = [_c_void_p, _c_void_p, ctypes.c_size_t, _c_void_p, ctypes.c_size_t]
+    lib.custen_slab_connect.restype = None
+    lib.custen_slab_field.argtypes, lib.custen_slab_field.restype = [_c_void_p, _c_int], ctypes.c_void_p
+    lib.custen_slab_rows.argtypes, lib.custen_slab_rows.restype = [_c_void_p], _c_int
+    for name in ("compute", "swap", "synchronize", "destroy"):
+        f = getattr(lib, f"custen_slab_{name}")
+        f.argtypes, f.restype = [_c_void_p], None
+    lib.custen_slab_run.argtypes, lib.custen_slab_run.restype = [_c_void_p, _c_int], None
+    lib.custen_slab_run_plain.argtypes, lib.custen_slab_run_plain.restype = [_c_void_p, _c_int], None
+    lib.custen_slab_time_run.argtypes, lib.custen_slab_time_run.restype = [_c_void_p, _c_int], ctypes.c_float
+    lib.custen_slab_error.argtypes, lib.custen_slab_error.restype = [_c_void_p], _c_int
+    lib.custen_slab_set_timeout.argtypes, lib.custen_slab_set_timeout.restype = [_c_void_p, ctypes.c_double], None
+    lib.custen_slab_last_path.argtypes, lib.custen_slab_last_path.restype = [_c_void_p], _c_int
+    lib.custen_mg_create.argtypes = [_c_int, _c_void_p, _c_int, _c_int, _c_int, _c_void_p] + [_c_int] * 7 + [ctypes.c_char_p, _c_void_p]
+    lib.custen_mg_create.restype = ctypes.c_void_p
+    lib.custen_mg_scatter.argtypes, lib.custen_mg_scatter.restype = [_c_void_p, _c_void_p], None
+    lib.custen_mg_gather.argtypes, lib.custen_mg_gather.restype = [_c_void_p, _c_void_p, _c_int], None
+    lib.custen_mg_fill_output.argtypes, lib.custen_mg_fill_output.restype = [_c_void_p, ctypes.c_double], None
+    for name in ("compute", "swap", "synchronize", "destroy"):
+        f = getattr(lib, f"custen_mg_{name}")
+        f.argtypes, f.restype = [_c_void_p], None
+    lib.custen_mg_run.argtypes, lib.custen_mg_run.restype = [_c_void_p, _c_int], None
+    lib.custen_mg_error.argtypes, lib.custen_mg_error.restype = [_c_void_p], _c_int
+    lib.custen_mg_slab.argtypes, lib.custen_mg_slab.restype = [_c_void_p, _c_int], ctypes.c_void_p
+    lib.custen_device_numa_node.argtypes, lib.custen_device_numa_node.restype = [_c_int], _c_int
+    lib.custen_host_alloc_near.argtypes, lib.custen_host_alloc_near.restype = [ctypes.c_size_t, _c_int, _c_void_p], ctypes.c_void_p
+    lib.custen_host_free_near.argtypes, lib.custen_host_free_near.restype = [_c_void_p, ctypes.c_size_t], None
+    lib.custen_link_probe.argtypes = [_c_void_p, _c_void_p, ctypes.c_size_t, _c_int, _c_int]
+    lib.custen_link_probe.restype = ctypes.c_float
     _lib = lib
     return lib
 

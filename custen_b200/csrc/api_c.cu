@@ -4,7 +4,12 @@
 #include "builtin_funs.cuh"
 #include "plan.h"
 
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <sys/mman.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 using namespace custen;
 
@@ -132,6 +137,21 @@ void custen_set_tuning(int force_fallback, int force_tile, int chunk_rows, int c
 }
 
 void custen_set_managed_policy(int policy) { set_managed_policy(policy); }
+void custen_set_handle_managed_policy(cuSten_c_handle* h, int policy) { set_handle_managed_policy(H(h), policy); }
+
+// unified-memory plumbing for callers without a CUDA runtime binding of their own (tools/um_probe.py, tests)
+int custen_mem_advise(const void* p, size_t bytes, int advice, int device)
+{
+    const cudaError_t e = cudaMemAdvise(p, bytes, (cudaMemoryAdvise)advice, device);
+    cudaGetLastError();
+    return (int)e;
+}
+int custen_mem_prefetch(const void* p, size_t bytes, int device)
+{
+    const cudaError_t e = cudaMemPrefetchAsync(p, bytes, device, 0);
+    cudaGetLastError();
+    return (int)e;
+}
 
 void custen_set_slab(cuSten_c_handle* h, const double* top, const double* bottom, int is_first, int is_last)
 {
@@ -211,6 +231,28 @@ void custen_peer_barrier(cuSten_c_handle* h, void* up_flags, void* down_flags, v
     checkError("custen_peer_barrier");
 }
 
+// field[r][c] = lo + (hi - lo) * u(seed, (row0 + r) * nx + c): counter-based, so any row can be regenerated on the CPU
+__global__ void custen_fill_hash_kernel(double* f, long long row0, long long count, int nx, unsigned long long seed, double lo,
+                                        double hi)
+{
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < count; i += stride)
+    {
+        unsigned long long z = seed + (unsigned long long)(row0 * nx + i) * 0x9E3779B97F4A7C15ull;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z = z ^ (z >> 31);
+        const double u = (double)(z >> 11) * (1.0 / 9007199254740992.0);
+        f[i] = __dadd_rn(lo, __dmul_rn(hi - lo, u));   // two roundings, like the numpy twin (no FMA contraction)
+    }
+}
+void custen_fill_hash(double* dev_field, long long row0, int rows, int nx, unsigned long long seed, double lo, double hi)
+{
+    custen_fill_hash_kernel<<<148 * 8, 256>>>(dev_field, row0, (long long)rows * nx, nx, seed, lo, hi);
+    checkError("custen_fill_hash");
+}
+
 void* custen_device_alloc(size_t bytes)
 {
     void* p = nullptr;
@@ -262,6 +304,106 @@ void* custen_host_alloc(size_t bytes)
     return p;
 }
 void custen_host_free(void* p) { cudaFreeHost(p); }
+
+// ---- pinned host memory next to a GPU, and what the host link can carry ------------------------------------------------
+// NUMA node the GPU hangs off (sysfs), or -1 when the platform does not say.
+int custen_device_numa_node(int device)
+{
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return -1;
+    }
+    for (char* c = bus; *c; ++c)
+        if (*c >= 'A' && *c <= 'Z') *c += 'a' - 'A';
+    char path[128];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE* f = fopen(path, "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    return node;
+}
+
+// Pinned host buffer whose pages are bound to the GPU's NUMA node (mmap + mbind + cudaHostRegister), so that the
+// staged pipeline of several ranks does not funnel every transfer through one socket's memory.  *node_out: the node
+// the pages were bound to, or -1 when binding was not possible (then this is an ordinary pinned allocation).
+// Free with custen_host_free_near.
+void* custen_host_alloc_near(size_t bytes, int device, int* node_out)
+{
+    const int node = custen_device_numa_node(device);
+    if (node_out) *node_out = -1;
+    const size_t len = (bytes + 4095) & ~(size_t)4095;
+    void* p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (p == MAP_FAILED) return nullptr;
+    if (node >= 0 && node < 64)
+    {
+        unsigned long mask = 1ul << node;
+        const int MPOL_BIND_ = 2;
+        if (syscall(SYS_mbind, p, len, MPOL_BIND_, &mask, sizeof(mask) * 8 + 1, 0) == 0 && node_out) *node_out = node;
+    }
+    memset(p, 0, len);   // first touch under the policy
+    if (cudaHostRegister(p, len, cudaHostRegisterPortable) != cudaSuccess)
+    {
+        cudaGetLastError();
+        munmap(p, len);
+        return nullptr;
+    }
+    return p;
+}
+void custen_host_free_near(void* p, size_t bytes)
+{
+    if (!p) return;
+    cudaHostUnregister(p);
+    cudaGetLastError();
+    munmap(p, (bytes + 4095) & ~(size_t)4095);
+}
+
+// Plain cudaMemcpyAsync in both directions at once between pinned host buffers and device scratch, `iters` times:
+// the ceiling the out-of-core pipeline is measured against (bench.py e2e.link_frac).  Returns milliseconds.
+float custen_link_probe(const void* host_src, void* host_dst, size_t bytes, int iters, int device)
+{
+    cudaSetDevice(device);
+    const size_t chunk = bytes < ((size_t)256 << 20) ? bytes : ((size_t)256 << 20);
+    void *d_in = nullptr, *d_out = nullptr;
+    cudaMalloc(&d_in, chunk);
+    cudaMalloc(&d_out, chunk);
+    cudaStream_t s_in, s_out;
+    cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking);
+    cudaEvent_t e0, e1, e2;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventCreate(&e2);
+    checkError("custen_link_probe: set-up");
+    cudaDeviceSynchronize();
+    cudaEventRecord(e0, s_in);
+    cudaStreamWaitEvent(s_out, e0, 0);
+    for (int it = 0; it < iters; ++it)
+        for (size_t o = 0; o < bytes; o += chunk)
+        {
+            const size_t n = bytes - o < chunk ? bytes - o : chunk;
+            cudaMemcpyAsync(d_in, (const char*)host_src + o, n, cudaMemcpyHostToDevice, s_in);
+            cudaMemcpyAsync((char*)host_dst + o, d_out, n, cudaMemcpyDeviceToHost, s_out);
+        }
+    cudaEventRecord(e2, s_out);
+    cudaStreamWaitEvent(s_in, e2, 0);
+    cudaEventRecord(e1, s_in);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaEventDestroy(e2);
+    cudaStreamDestroy(s_in);
+    cudaStreamDestroy(s_out);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    checkError("custen_link_probe");
+    return ms;
+}
 
 void* custen_managed_alloc(size_t bytes)
 {

@@ -41,6 +41,17 @@ struct Band
     const double* aux1;
     double p0, p1;
     int weno;
+    // Slab time stepping (multi-GPU layer, slab.cu): completion counters of this slab and of its neighbours.  All null
+    // when unused.  The sweep's producer warp waits for a neighbour only before it fetches that neighbour's halo rows
+    // (or lets the consumers overwrite rows that neighbour may still be reading); the last CTA to finish publishes this
+    // slab's new sweep count to both neighbours.  No separate barrier kernel.
+    const unsigned long long* wait_up;    // word in this slab's memory the slab above publishes its sweep count into
+    const unsigned long long* wait_down;  // ... the slab below
+    unsigned long long* signal_up;        // words in the neighbours' memory this slab publishes its own count into
+    unsigned long long* signal_down;
+    unsigned long long* sync_local;       // [0] sweeps completed by this slab, [1] CTAs finished in the current launch,
+                                          // [2] sticky time-out flag, [3] time-out in ns (0 = wait for ever)
+    int guard_top, guard_bottom;          // the band's first / last rows that a neighbour reads as its halo
 };
 
 // Which kernel family served a launch (reported through the C ABI for tests / bench).

@@ -120,8 +120,27 @@ static int sm_count()
     return per_dev[dev];
 }
 
+// Slab time stepping on the fallback road (odd nx, unaligned rows): the plain-load kernel has no producer warp to do the
+// waiting, so one thread waits in front of it and one publishes behind it.
+__global__ void slab_wait_kernel(const __grid_constant__ Band b)
+{
+    const unsigned long long sweep = *(volatile unsigned long long*)b.sync_local;
+    if (b.wait_up) slab_wait(b.wait_up, sweep, b.sync_local);
+    if (b.wait_down) slab_wait(b.wait_down, sweep, b.sync_local);
+}
+__global__ void slab_signal_kernel(const __grid_constant__ Band b)
+{
+    __threadfence_system();
+    volatile unsigned long long* loc = b.sync_local;
+    const unsigned long long done = loc[0] + 1ull;
+    loc[0] = done;
+    if (b.signal_up) st_release_sys(b.signal_up, done);
+    if (b.signal_down) st_release_sys(b.signal_down, done);
+}
+
 static int launch_fallback(const Band& b, cudaStream_t st)
 {
+    if (b.sync_local) slab_wait_kernel<<<1, 1, 0, st>>>(b);
     const int Reff = b.H - 1 - b.L, Beff = b.V - 1 - b.T;
     const size_t smem = ((size_t)(FB_BX + b.L + Reff) * (FB_BY + b.T + Beff) + b.ncoef) * sizeof(double);
     dim3 grid((b.nx + FB_BX - 1) / FB_BX, (b.rows + FB_BY - 1) / FB_BY), block(FB_BX, FB_BY);
@@ -137,6 +156,7 @@ static int launch_fallback(const Band& b, cudaStream_t st)
         FB_CASE(0) FB_CASE(1) FB_CASE(2) FB_CASE(3) FB_CASE(4)
     }
 #undef FB_CASE
+    if (b.sync_local) slab_signal_kernel<<<1, 1, 0, st>>>(b);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return PATH_FALLBACK;
 }
@@ -155,22 +175,48 @@ template <> struct AccGeom<1, 9> { static constexpr int NT = 512, CPT = 1, SR = 
 
 // Work decomposition: column strips x row chunks, chunk height chosen so that the item count is (just under)
 // a whole number of waves of resident CTAs.
-LaunchGeom plan_stream_launch(StreamArgs& a, const void* kernel, int threads, size_t smem, int max_cps)
+// The occupancy query and the shared-memory opt-in depend only on (kernel, device, request): they are made once and
+// remembered, so a steady-state launch issues no runtime calls besides the launch itself (and can be stream-captured).
+struct LaunchMemo
 {
+    const void* kernel;
+    int device, threads, max_cps, tuned_cps;
+    size_t smem_in, smem_out;
+    int cps;
+};
+static LaunchMemo g_memo[256];
+static std::atomic<int> g_memo_n{0};
+static std::atomic_flag g_memo_lock = ATOMIC_FLAG_INIT;
+
+static void resolve_occupancy(const void* kernel, int threads, size_t& smem, int max_cps, int& cps)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int tuned = tuning().ctas_per_sm;
+    const int n = g_memo_n.load(std::memory_order_acquire);
+    for (int i = 0; i < n; ++i)
+    {
+        const LaunchMemo& m = g_memo[i];
+        if (m.kernel == kernel && m.device == dev && m.threads == threads && m.smem_in == smem && m.max_cps == max_cps &&
+            m.tuned_cps == tuned)
+        {
+            smem = m.smem_out;
+            cps = m.cps;
+            return;
+        }
+    }
+    const size_t smem_in = smem;
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int cps = tuning().ctas_per_sm;
+    cps = tuned;
     if (cps <= 0)
     {
         cps = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, kernel, threads, smem);
         if (max_cps > 0 && cps > max_cps) cps = max_cps;
         if (cps < 1) cps = 1;
-    }
-    // The geometry wants exactly `cps` CTAs on every SM.  If more would fit, the hardware scheduler is free to
-    // double up on some SMs and leave others empty (measured: bistable 290 / 350 Gpoints/s for the same launch), so
-    // the request is padded until cps + 1 no longer fit.
-    if (tuning().ctas_per_sm <= 0)
-    {
+        // The geometry wants exactly `cps` CTAs on every SM.  If more would fit, the hardware scheduler is free to
+        // double up on some SMs and leave others empty (measured: bistable 290 / 350 Gpoints/s for the same launch), so
+        // the request is padded until cps + 1 no longer fit.
         const size_t sm_bytes = 228 * 1024, per_cta_reserved = 1024;
         const size_t need = sm_bytes / (size_t)(cps + 1) - per_cta_reserved + 256;
         if (smem < need && (need + per_cta_reserved) * (size_t)cps <= sm_bytes && need <= 227 * 1024)
@@ -179,6 +225,20 @@ LaunchGeom plan_stream_launch(StreamArgs& a, const void* kernel, int threads, si
             cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         }
     }
+    while (g_memo_lock.test_and_set(std::memory_order_acquire)) {}
+    const int k = g_memo_n.load(std::memory_order_relaxed);
+    if (k < 256)
+    {
+        g_memo[k] = LaunchMemo{kernel, dev, threads, max_cps, tuned, smem_in, smem, cps};
+        g_memo_n.store(k + 1, std::memory_order_release);
+    }
+    g_memo_lock.clear(std::memory_order_release);
+}
+
+LaunchGeom plan_stream_launch(StreamArgs& a, const void* kernel, int threads, size_t smem, int max_cps)
+{
+    int cps = 1;
+    resolve_occupancy(kernel, threads, smem, max_cps, cps);
     const int ncta = sm_count() * cps;
     const Band& b = a.b;
     int ch = tuning().chunk_rows;
@@ -197,6 +257,7 @@ LaunchGeom plan_stream_launch(StreamArgs& a, const void* kernel, int threads, si
     a.chunk_rows = ch;
     a.nchunks = (b.rows + ch - 1) / ch;
     a.nitems = a.nstrips * a.nchunks;
+    a.edge_last = b.sync_local != nullptr;
     LaunchGeom g;
     g.grid = a.nitems < ncta ? a.nitems : ncta;
     g.threads = threads;
@@ -227,17 +288,22 @@ static FunRegistration* g_registry = nullptr;
 void register_fun(FunRegistration* r)
 {
     r->next = g_registry;  // static-initialisation time: single threaded, no CUDA calls here
-    r->dev_ptr = nullptr;
+    for (int d = 0; d < kMaxRegDevices; ++d) r->dev_ptr[d] = nullptr;
     g_registry = r;
 }
 
+// A device function's address is a per-device fact: it is read (cudaMemcpyFromSymbol, in the registering translation
+// unit) once per device, on the device the launch is about to happen on.
 static InlineLauncher find_inline(const void* func, int dir)
 {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= kMaxRegDevices) return nullptr;
     for (FunRegistration* r = g_registry; r; r = r->next)
     {
         if (r->dir != dir) continue;
-        if (!r->dev_ptr) r->dev_ptr = r->resolve();
-        if (r->dev_ptr == func) return r->launch;
+        if (!r->dev_ptr[dev]) r->dev_ptr[dev] = r->resolve();
+        if (r->dev_ptr[dev] == func) return r->launch;
     }
     return nullptr;
 }

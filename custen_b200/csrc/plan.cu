@@ -90,6 +90,7 @@ static void plan_create_impl(cuSten_t* h, Spec spec, int nstreams, int deviceNum
 
     Plan* p = (Plan*)calloc(1, sizeof(Plan));
     p->spec = spec;
+    p->managed_policy = -1;
     uintptr_t* tail = reinterpret_cast<uintptr_t*>(h->streams + nstreams);
     tail[0] = kMagic;
     tail[1] = reinterpret_cast<uintptr_t>(p);
@@ -178,6 +179,7 @@ void plan_swap(cuSten_t* h, double* dataInput)
 }
 
 static void unadvise(Plan* p, int dev);
+static void join_all(cuSten_t* h, Plan* p);
 
 static void release_staging(Plan* p)
 {
@@ -195,6 +197,7 @@ static void release_staging(Plan* p)
     }
     if (p->d_coef) cudaFree(p->d_coef);
     p->d_coef = nullptr;
+    p->coef_cap = 0;
     p->events_ready = 0;
     p->stage_rows = 0;
 }
@@ -207,9 +210,11 @@ void plan_destroy(cuSten_t* h)
     if (p)
     {
         // staging buffers may still be in flight: drain this handle's streams before freeing them
-        if (p->stage_rows || p->d_coef)
+        if (p->stage_rows || p->d_coef || p->spread)
             for (int s = 0; s < 3; ++s) cudaStreamSynchronize(h->streams[s]);
         release_staging(p);
+        if (p->join_ready)
+            for (int k = 0; k < 3; ++k) cudaEventDestroy(p->ev_join[k]);
         if (p->zc_n) unadvise(p, h->deviceNum);
         free(p);
     }
@@ -309,6 +314,17 @@ static Band make_band(const cuSten_t* h, const Plan* p, const double* coef, int 
         }
         if (b.T == 0) b.have_top = 0;
         if (b.B == 0) b.have_bottom = 0;
+        if (p->slab_enabled && p->sync_local && at_top && at_bottom)
+        {
+            // the slab above reads my first B rows as its bottom halo, the slab below my last T rows as its top halo
+            b.sync_local = p->sync_local;
+            b.wait_up = p->sync_wait_up;
+            b.wait_down = p->sync_wait_down;
+            b.signal_up = p->sync_signal_up;
+            b.signal_down = p->sync_signal_down;
+            b.guard_top = b.B;
+            b.guard_bottom = b.T;
+        }
     }
     return b;
 }
@@ -355,6 +371,8 @@ static void compute_resident(cuSten_t* h, Plan* p, const double* coef)
         return;
     }
     p->last_mode = 1;
+    join_all(h, p);
+    p->spread = 1;
     for (int t = 0; t < h->numTiles; ++t)
     {
         const Band b = make_band(h, p, coef, t, t);
@@ -461,32 +479,47 @@ static bool advised(const Plan* p, const Span& s)
     return false;
 }
 
-static int managed_policy_flag = 0;
-void set_managed_policy(int policy) { managed_policy_flag = policy; }
-
-// The pipeline spreads a call over the three rotating streams; the single-launch roads use streams[0] only.  When
-// one follows the other, streams[0] first waits for whatever the previous call left running on the other two.
-static void join_streams(cuSten_t* h)
+static int managed_policy_default = 0;   // what a handle without its own setting follows
+void set_managed_policy(int policy) { managed_policy_default = policy; }
+void set_handle_managed_policy(cuSten_t* h, int policy)
 {
-    for (int k = 1; k <= 2; ++k)
+    if (Plan* p = plan_of(h)) p->managed_policy = policy;
+}
+static int managed_policy_of(const Plan* p) { return p->managed_policy >= 0 ? p->managed_policy : managed_policy_default; }
+
+// Ordering between consecutive calls on one handle.  The single-launch roads use streams[0] only; the tile pipelines
+// (per-tile resident launches, the unified-memory prefetch pipeline, the staged pipeline for host grids) spread a call
+// over all three streams.  Whenever the previous call or the coming one is of the second kind, the call starts with a
+// three-way join: every stream waits for whatever the previous call left running on the other two.  Without it the
+// next call's uploads could overwrite a staging slot a kernel is still reading, or read a host array the previous
+// call's downloads are still writing (Compute, Swap, Compute with no device sync in between).
+static void join_all(cuSten_t* h, Plan* p)
+{
+    if (p->joined_now) return;  // this call has already joined (plan_compute does it first when the previous call was spread)
+    p->joined_now = 1;
+    if (!p->join_ready)
     {
-        cudaEventRecord(h->events[k - 1], h->streams[k]);
-        cudaStreamWaitEvent(h->streams[0], h->events[k - 1], 0);
+        for (int k = 0; k < 3; ++k) cudaEventCreateWithFlags(&p->ev_join[k], cudaEventDisableTiming);
+        p->join_ready = 1;
     }
+    for (int k = 0; k < 3; ++k) cudaEventRecord(p->ev_join[k], h->streams[k]);
+    for (int k = 0; k < 3; ++k)
+        for (int j = 0; j < 3; ++j)
+            if (j != k) cudaStreamWaitEvent(h->streams[k], p->ev_join[j], 0);
+    p->spread = 0;
 }
 
 static void compute_managed(cuSten_t* h, Plan* p, const double* coef, MemKind kcoef, bool offload)
 {
     const int dev = h->deviceNum;
     Span sp[kMaxSpans];
-    const int nsp = (managed_policy_flag == 0 && tiles_contiguous(h)) ? managed_spans(h, sp) : 0;
+    const int nsp = (managed_policy_of(p) == 0 && tiles_contiguous(h)) ? managed_spans(h, sp) : 0;
     const bool spans_complete = nsp > 0;
 
     if (spans_complete && !offload)
     {
         if (left_at(p, sp, nsp, 1))
         {
-            if (p->last_mode == 2) join_streams(h);
             if (kcoef == MK_MANAGED) prefetch(coef, (size_t)p->ncoef * sizeof(double), dev, h->streams[0]);
             compute_resident(h, p, coef);
             p->last_mode = 4;
@@ -503,6 +536,17 @@ static void compute_managed(cuSten_t* h, Plan* p, const double* coef, MemKind kc
             for (int k = 0; k < nsp && ok; ++k)
             {
                 if (advised(p, sp[k])) continue;
+                // a range the caller has already given a preferred location keeps it: the zero-copy road only takes
+                // ranges nobody has advised (this handle's own advice is withdrawn again by unadvise())
+                int pref = cudaInvalidDeviceId;
+                if (cudaMemRangeGetAttribute(&pref, sizeof pref, cudaMemRangeAttributePreferredLocation, sp[k].p, sp[k].bytes) !=
+                        cudaSuccess ||
+                    pref != cudaInvalidDeviceId)
+                {
+                    cudaGetLastError();
+                    ok = false;
+                    break;
+                }
                 ok = cudaMemAdvise(sp[k].p, sp[k].bytes, cudaMemAdviseSetPreferredLocation, cudaCpuDeviceId) == cudaSuccess &&
                      cudaMemAdvise(sp[k].p, sp[k].bytes, cudaMemAdviseSetAccessedBy, dev) == cudaSuccess;
                 if (ok && p->zc_n < kMaxSpans)
@@ -514,8 +558,7 @@ static void compute_managed(cuSten_t* h, Plan* p, const double* coef, MemKind kc
             }
             if (ok)
             {
-                if (p->last_mode == 2) join_streams(h);
-                if (kcoef == MK_MANAGED) prefetch(coef, (size_t)p->ncoef * sizeof(double), dev, h->streams[0]);
+                    if (kcoef == MK_MANAGED) prefetch(coef, (size_t)p->ncoef * sizeof(double), dev, h->streams[0]);
                 cudaStream_t st = h->streams[0];
                 compute_resident(h, p, coef);
                 p->last_mode = 5;
@@ -535,6 +578,8 @@ static void compute_managed(cuSten_t* h, Plan* p, const double* coef, MemKind kc
     }
 
     if (p->zc_n) unadvise(p, dev);
+    join_all(h, p);
+    p->spread = 1;
     p->last_mode = 2;
     p->res_where = 0;
     if (spans_complete && !offload) note_left_at(p, sp, nsp, 1);  // the pipeline below leaves every tile on the GPU
@@ -606,6 +651,10 @@ static void compute_staged(cuSten_t* h, Plan* p, const double* coef)
         p->events_ready = 1;
     }
 
+    // the previous call on this handle may still be computing on / downloading from the slots, or (after a Swap)
+    // writing the host array this call uploads from
+    join_all(h, p);
+    p->spread = 1;
     cudaStream_t s_comp = h->streams[0], s_load = h->streams[1], s_unload = h->streams[2];
     const int slots = h->numTiles < kSlots ? h->numTiles : kSlots;
     const size_t row_bytes = nx * sizeof(double);
@@ -652,6 +701,18 @@ static void compute_staged(cuSten_t* h, Plan* p, const double* coef)
     check("Error in staged tile pipeline", dev);
 }
 
+int plan_launch_slab(cuSten_t* h, cudaStream_t stream)
+{
+    Plan* p = plan_of(h);
+    const Spec& s = p->spec;
+    const double* coef = s.fun ? h->coe : h->weights;
+    const Band b = make_band(h, p, coef, 0, h->numTiles - 1);
+    p->last_path = launch_band(b, stream);
+    p->last_mode = 0;
+    check("Error computing slab", h->deviceNum);
+    return p->last_path;
+}
+
 void plan_compute(cuSten_t* h, bool offload)
 {
     cudaSetDevice(h->deviceNum);
@@ -674,16 +735,24 @@ void plan_compute(cuSten_t* h, bool offload)
         exit(EXIT_FAILURE);
     }
 
+    // the previous call left work on all three streams: this one starts behind all of it
+    if (p->spread) join_all(h, p);
+
     // coefficients living in plain host memory are snapshotted to the device, stream-ordered
     if (kcoef == MK_HOST)
     {
-        if (!p->d_coef)
+        if (p->coef_cap < (size_t)p->ncoef)
         {
-            cudaMalloc(&p->d_coef, 1024 * sizeof(double));
+            if (p->d_coef)
+            {
+                for (int k = 0; k < 3; ++k) cudaStreamSynchronize(h->streams[k]);
+                cudaFree(p->d_coef);
+            }
+            p->coef_cap = p->ncoef > 64 ? (size_t)p->ncoef : 64;
+            cudaMalloc(&p->d_coef, p->coef_cap * sizeof(double));
             check("Allocating coefficient buffer", h->deviceNum);
         }
-        const int n = p->ncoef < 1024 ? p->ncoef : 1024;
-        cudaMemcpyAsync(p->d_coef, coef, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->streams[0]);
+        cudaMemcpyAsync(p->d_coef, coef, (size_t)p->ncoef * sizeof(double), cudaMemcpyHostToDevice, h->streams[0]);
         // every stream that may launch a kernel must see the snapshot
         cudaEventRecord(h->events[1], h->streams[0]);
         cudaStreamWaitEvent(h->streams[1], h->events[1], 0);
@@ -695,6 +764,7 @@ void plan_compute(cuSten_t* h, bool offload)
     if (kin == MK_HOST || kout == MK_HOST) compute_staged(h, p, coef);
     else if (kin == MK_MANAGED || kout == MK_MANAGED) compute_managed(h, p, coef, kcoef, offload);
     else compute_resident(h, p, coef);
+    p->joined_now = 0;
 }
 
 // ---- host-logic probe (no CUDA) --------------------------------------------------------------------------------

@@ -47,6 +47,12 @@ struct Plan
     const double* slab_bottom;
     int slab_first, slab_last;   // this slab touches the physical top / bottom of the global grid
     int slab_enabled;
+    // slab time stepping (slab.cu): neighbour completion counters handed to the kernels through Band (engine.h)
+    const unsigned long long* sync_wait_up;
+    const unsigned long long* sync_wait_down;
+    unsigned long long* sync_signal_up;
+    unsigned long long* sync_signal_down;
+    unsigned long long* sync_local;
     // staging for host-resident grids
     double* d_in[kSlots];
     double* d_out[kSlots];
@@ -54,6 +60,12 @@ struct Plan
     size_t stage_rows;           // rows each d_in slot can hold
     cudaEvent_t ev_loaded[kSlots], ev_done[kSlots], ev_unloaded[kSlots];
     int events_ready;
+    size_t coef_cap;             // doubles d_coef can hold
+    // ordering between consecutive calls on one handle: `spread` = the previous call left work on streams[1] / [2]
+    // as well as streams[0]; the next call then starts with a three-way join (ev_join)
+    cudaEvent_t ev_join[3];
+    int join_ready, spread, joined_now;
+    int managed_policy;          // per handle: -1 follow the process default, else as custen_set_managed_policy
 };
 
 Plan* plan_of(cuSten_t* h);
@@ -66,11 +78,16 @@ void plan_create_weno(cuSten_t* h, int deviceNum, int numTiles, int nx, int ny, 
 void plan_swap(cuSten_t* h, double* dataInput);
 void plan_destroy(cuSten_t* h);
 void plan_compute(cuSten_t* h, bool offload);
+// Slab layer: sweep the handle's whole (device-resident) grid as one band on `stream`, halo rows and neighbour
+// counters as set in the plan's slab_* / sync_* fields.  Returns the Path used.
+int plan_launch_slab(cuSten_t* h, cudaStream_t stream);
 
 MemKind classify(const void* p);
 // 0 (default): unified-memory grids take the resident / zero-copy roads when they apply; 1: always the reference's
 // prefetch pipeline
 void set_managed_policy(int policy);
+// the same per handle (-1: follow the process default again)
+void set_handle_managed_policy(cuSten_t* h, int policy);
 
 // What one launch would cover, for tests of the host logic (see debug_bands in plan.cu).
 struct BandDesc

@@ -85,6 +85,70 @@ __device__ __forceinline__ void consumer_bar(int nthreads)
     asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
 }
 
+// ---- slab time stepping: neighbour counters (Band::wait_* / signal_* / sync_local) ------------------------------
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// Spin until the neighbour has published at least `target` finished sweeps.  A neighbour that never arrives (a bug, a
+// dead rank) must not hang the GPU: after sync_local[3] nanoseconds the wait gives up and raises the sticky flag
+// sync_local[2], which the host reports (custen_slab_error).  The proxy fence orders the TMA (async proxy) reads of
+// the neighbour's rows behind the acquire.
+__device__ __forceinline__ void slab_wait(const unsigned long long* flag, unsigned long long target,
+                                          unsigned long long* local)
+{
+    if (ld_acquire_sys(flag) < target)
+    {
+        const unsigned long long limit = *(volatile unsigned long long*)(local + 3);
+        const unsigned long long t0 = global_timer_ns();
+        unsigned polls = 0;
+        while (ld_acquire_sys(flag) < target)
+        {
+            if ((++polls & 255u) == 0 && limit && global_timer_ns() - t0 > limit)
+            {
+                *(volatile unsigned long long*)(local + 2) = 1ull;
+                break;
+            }
+        }
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");
+}
+// End of a sweep: called by the NT consumer threads once their last store has been issued.
+__device__ __forceinline__ void slab_epilogue(const Band& b, int nconsumers)
+{
+    if (!b.sync_local) return;
+    __threadfence_system();
+    consumer_bar(nconsumers);
+    if (threadIdx.x == 0)
+    {
+        __threadfence_system();
+        const unsigned long long prev = atomicAdd(b.sync_local + 1, 1ull);
+        if (prev == (unsigned long long)gridDim.x - 1)
+        {
+            __threadfence_system();
+            volatile unsigned long long* loc = b.sync_local;
+            loc[1] = 0ull;
+            const unsigned long long done = loc[0] + 1ull;
+            loc[0] = done;
+            if (b.signal_up) st_release_sys(b.signal_up, done);
+            if (b.signal_down) st_release_sys(b.signal_down, done);
+        }
+    }
+}
+
 // ---- geometry shared by host and device ----------------------------------------------------------------------
 
 struct StreamArgs
@@ -97,7 +161,16 @@ struct StreamArgs
     int PFX;            // rows kept in front of each stage (tile family: V - 1, acc family: 0)
     int nstrips, nchunks, chunk_rows, nitems;
     int stage_doubles;  // (PFX + SR) * PW
+    int edge_last;      // slab time stepping: the first and last row chunk (the ones that touch halo rows) are swept last
 };
+
+// Order in which a CTA walks the row chunks.  In slab mode the two chunks that need a neighbour's rows come last, so
+// that by the time a producer has to wait for a neighbour, the neighbour has normally long finished its previous sweep.
+__device__ __forceinline__ int chunk_of(const StreamArgs& a, int q)
+{
+    if (!a.edge_last || a.nchunks <= 2) return q;
+    return q < a.nchunks - 2 ? q + 1 : (q == a.nchunks - 2 ? 0 : a.nchunks - 1);
+}
 
 struct StageDesc
 {
@@ -124,7 +197,7 @@ __device__ __forceinline__ int cta_stage_count(const StreamArgs& a)
     int total = 0;
     for (int item = blockIdx.x; item < a.nitems; item += gridDim.x)
     {
-        const int chunk = item / a.nstrips;
+        const int chunk = chunk_of(a, item / a.nstrips);
         const int out_lo = chunk * a.chunk_rows;
         const int out_hi = min(out_lo + a.chunk_rows, a.b.rows);
         total += (out_hi - out_lo + a.b.T + a.Beff + SR - 1) / SR;
@@ -146,17 +219,34 @@ __device__ __forceinline__ void producer_loop(const StreamArgs& a, unsigned char
     const uint32_t stage_bytes = (uint32_t)a.stage_doubles * 8u;
     const uint32_t pitch_bytes = (uint32_t)a.PW * 8u;
 
+    // slab time stepping: this launch is sweep number `sweep` of the slab; a neighbour must have finished its sweep
+    // `sweep - 1` before its halo rows are read (they are that sweep's output) and before the rows it reads from this
+    // slab (the guard rows, that sweep's input) are overwritten
+    const bool slab = b.sync_local != nullptr;
+    const unsigned long long sweep = slab ? *(volatile unsigned long long*)b.sync_local : 0ull;
+    bool ok_up = !slab || !b.wait_up, ok_down = !slab || !b.wait_down;
+
     int s = 0;
     uint32_t ph = 0;
     for (int item = blockIdx.x; item < a.nitems; item += gridDim.x)
     {
         const int strip = item % a.nstrips;
-        const int chunk = item / a.nstrips;
+        const int chunk = chunk_of(a, item / a.nstrips);
         const int x0 = strip * a.TW;
         const int out_lo = chunk * a.chunk_rows;
         const int out_hi = min(out_lo + a.chunk_rows, b.rows);
         const int in_lo = out_lo - b.T;
         const int in_hi = out_hi + a.Beff;
+        if (!ok_up && (in_lo < 0 || out_lo < b.guard_top))
+        {
+            slab_wait(b.wait_up, sweep, b.sync_local);
+            ok_up = true;
+        }
+        if (!ok_down && (in_hi > b.rows || out_hi > b.rows - b.guard_bottom))
+        {
+            slab_wait(b.wait_down, sweep, b.sync_local);
+            ok_down = true;
+        }
 
         // unwrapped column range this strip needs: [u0, u1)
         const int xe = min(x0 + a.TW, b.nx);
@@ -373,6 +463,7 @@ __global__ void __launch_bounds__(NT + 32, MINB) stream_acc_kernel(const __grid_
         if (lane == 0) mbar_arrive(empty0 + 8 * s);
         if (++s == NS) { s = 0; ph ^= 1; }
     }
+    slab_epilogue(b, NT);
 }
 
 // ---- stream_tile_kernel: a contiguous window in shared memory, handed to an operator --------------------------
@@ -571,6 +662,7 @@ __global__ void __launch_bounds__(NT + 32, MINB) stream_tile_kernel(const __grid
         if (t == 0) mbar_arrive(empty0 + 8 * s);
         if (++s == NS) { s = 0; ph ^= 1; }
     }
+    slab_epilogue(b, NT);
 }
 
 // ---- launch plumbing shared by the library and by registering translation units ------------------------------
@@ -662,12 +754,13 @@ inline void launch_inline_xy(StreamArgs& a, cudaStream_t st)
 }
 
 // Registry of inlined instances, keyed by the device address of the user function.
+constexpr int kMaxRegDevices = 16;
 struct FunRegistration
 {
     int dir;                               // Dir
-    const void* (*resolve)();              // reads the device pointer (cudaMemcpyFromSymbol), called lazily
+    const void* (*resolve)();              // reads the device pointer on the current device (cudaMemcpyFromSymbol)
     InlineLauncher launch;
-    const void* dev_ptr;                   // filled on first use
+    const void* dev_ptr[kMaxRegDevices];   // per device, filled on first use there
     FunRegistration* next;
 };
 void register_fun(FunRegistration* r);     // defined in kernels.cu

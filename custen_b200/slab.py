@@ -1,20 +1,23 @@
-"""Multi-GPU y-slab layer (new; the reference is single-GPU).
+"""Multi-GPU y-slab layer (new; the reference is single-GPU) - Python side.
 
 One process per GPU.  The global ny x nx grid is cut into `world` contiguous y-slabs; rank g owns rows
-[g*ny/world, (g+1)*ny/world).  A sweep needs only the T rows above and the B rows below each slab — the role
-the reference gives its per-tile boundaryTop / boundaryBottom pointers (custenCreateDestroy2DXYp.cu:194-228).
-Two transports, both feeding `custen_set_slab`:
+[g*ny/world, (g+1)*ny/world) of both field buffers.  A sweep needs only the T rows above and the B rows below each
+slab - the role the reference gives its per-tile boundaryTop / boundaryBottom pointers
+(custenCreateDestroy2DXYp.cu:194-228).  Two transports:
 
-  exchange   every step, the edge rows travel with torch.distributed P2P ops (NCCL send/recv on GPUs, gloo in
-             the CPU tests) into local halo buffers; a ring for periodic variants, an open line otherwise.
-  peer       the neighbours' arrays are mapped once through CUDA IPC and the stencil kernel's TMA producer
-             reads the halo rows straight out of peer memory over NVLink, so the transfer is folded into the
-             sweep itself; a step then only needs a barrier.
+  peer       (default) everything happens in the CUDA library (custen_b200/csrc/slab.cu, `custen_slab_*`): the
+             neighbours' buffers are mapped once through CUDA IPC, the stencil kernel's TMA producer reads the halo rows
+             straight out of peer memory over NVLink, and the wait for the neighbour sits inside the sweep kernel, in
+             front of the halo rows only.  Python's part is the rendezvous: moving 64-byte IPC handles between ranks.
+  exchange   every step the edge rows travel with torch.distributed P2P ops (NCCL send/recv on GPUs, gloo in the CPU
+             tests) into local halo buffers; a ring for periodic variants, an open line otherwise.  Kept as the
+             library-collective baseline the peer transport is measured against.
 
 X variants need neither (rows are independent).
 """
 import ctypes
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -63,106 +66,144 @@ def exchange_halos(local, T, B, top_buf, bottom_buf, rank, world, periodic, grou
             w.wait()
 
 
-class SlabStencil:
-    """A cuSten handle over this rank's slab of a global grid, with its halo transport.
+class _DeviceView:
+    """Zero-copy torch view of a raw device pointer (CUDA array interface)."""
 
-    variant, coef, H..B, fun: as custen_b200.Stencil2D.  `inp` / `out` are this rank's CUDA tensors (rows x nx).
-    transport: "exchange" (NCCL send/recv into halo buffers) or "peer" (IPC-mapped neighbour memory).
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+def device_view(ptr, shape, device):
+    return torch.as_tensor(_DeviceView(ptr, shape), device=device)
+
+
+class SlabStencil:
+    """This rank's slab of a global grid, time-stepped with Compute + Swap.
+
+    variant, coef, H..B, fun: as custen_b200.Stencil2D (coef: numpy array).  The slab owns both field buffers;
+    `input` / `output` are torch views of the current roles, `step()` = one sweep, `swap()` trades the roles,
+    `run(n)` = n x (sweep + swap).
     """
 
-    def __init__(self, variant, nx, ny_global, inp, out, coef, transport="exchange", group=None, **kw):
+    def __init__(self, variant, nx, ny_global, coef, transport="peer", group=None, device=None, H=1, L=0, R=0, V=1, T=0,
+                 B=0, fun=None, numCoe=None, numTiles=1):
         from . import api, _lib
+        self.lib = lib = _lib.load()
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.group = group
+        self.variant = variant
         self.periodic = not variant.replace("Fun", "").endswith("np")
         self.is_x = not variant.startswith("XY") and variant.startswith("X")
         lo, hi = slab_rows(ny_global, self.world, self.rank)
-        self.rows, self.nx = hi - lo, nx
-        self.T, self.B = (0, 0) if self.is_x else (kw.get("T", 0), kw.get("B", 0))
-        self.inp, self.out = inp, out
+        self.row0, self.rows, self.nx = lo, hi - lo, nx
+        self.T, self.B = (0, 0) if self.is_x else (T, B)
         self.transport = transport
-        self.st = api.Stencil2D(variant, nx, self.rows, out, inp, coef, deviceNum=inp.device.index or 0, **kw)
-        self._mapped = []
+        dev = torch.cuda.current_device() if device is None else device
+        self.device = torch.device("cuda", dev)
+        coef = np.ascontiguousarray(coef, dtype=np.float64)
+        ncoef = int(numCoe) if numCoe is not None else coef.size
+        fp = api.builtin_fun(fun) if isinstance(fun, str) else fun
+        self.slab = None
         up, down = neighbours(self.rank, self.world, self.periodic)
-        first, last = self.rank == 0, self.rank == self.world - 1
-        if self.is_x:
-            return
-        if transport == "exchange" or self.world == 1:
-            self.top = torch.empty((max(self.T, 1), nx), dtype=torch.float64, device=inp.device)
-            self.bottom = torch.empty((max(self.B, 1), nx), dtype=torch.float64, device=inp.device)
-            self.st.set_slab(self.top, self.bottom, first, last)
-        elif transport == "peer":
-            lib = _lib.load()
-            mine = (ctypes.c_char * 64)()
-            off = ctypes.c_size_t(0)
-            # IPC handles name the allocation a pointer lives in; `off` is the tensor's byte offset inside it
-            lib.custen_ipc_export(inp.data_ptr(), ctypes.addressof(mine), ctypes.byref(off))
-            handles, offs = [None] * self.world, [None] * self.world
-            dist.all_gather_object(handles, bytes(mine), group=group)
-            dist.all_gather_object(offs, int(off.value), group=group)
+        if transport == "peer":
+            self.slab = lib.custen_slab_create(_lib.VARIANTS.index(variant), dev, self.rank, self.world, nx, ny_global,
+                                               coef.ctypes.data, ncoef, H, L, R, V, T, B, fp)
+            if self.world > 1:
+                mine, off = (ctypes.c_char * 64)(), ctypes.c_size_t(0)
+                lib.custen_slab_export(self.slab, ctypes.addressof(mine), ctypes.byref(off))
+                handles, offs = [None] * self.world, [None] * self.world
+                dist.all_gather_object(handles, bytes(mine), group=group)
+                dist.all_gather_object(offs, int(off.value), group=group)
+                keep = []
 
-            opened = {}
-
-            def peer_ptr(r):
-                if r not in opened:  # with two ranks the slab above and the slab below are the same peer
+                def arg(r):
+                    if r is None:
+                        return None, 0
                     buf = (ctypes.c_char * 64).from_buffer_copy(handles[r])
-                    opened[r] = lib.custen_ipc_open(ctypes.addressof(buf))
-                    self._mapped.append(opened[r])
-                return opened[r] + offs[r]
+                    keep.append(buf)
+                    return ctypes.addressof(buf), offs[r]
 
-            row = nx * 8
-            top = peer_ptr(up) + (self.rows - self.T) * row if up is not None else 0
-            bottom = peer_ptr(down) if down is not None else 0
-            self.st.set_slab(top, bottom, first, last)
-            # neighbour barrier flags (2 x u64 per rank), exchanged the same way
-            self._flags = lib.custen_device_alloc(16)
-            fh = (ctypes.c_char * 64)()
-            lib.custen_ipc_export(self._flags, ctypes.addressof(fh), None)
-            fhandles = [None] * self.world
-            dist.all_gather_object(fhandles, bytes(fh), group=group)
-            fopened = {}
-
-            def flag_ptr(r):
-                if r is None:
-                    return None
-                if r not in fopened:
-                    buf = (ctypes.c_char * 64).from_buffer_copy(fhandles[r])
-                    fopened[r] = lib.custen_ipc_open(ctypes.addressof(buf))
-                    self._mapped.append(fopened[r])
-                return fopened[r]
-
-            self._up_flags, self._down_flags = flag_ptr(up), flag_ptr(down)
-            self._epoch = 0
-            dist.barrier(group=group)
+                (uh, uo), (dh, do) = arg(up), arg(down)
+                lib.custen_slab_connect(self.slab, uh, uo, dh, do)
+                dist.barrier(group=group)
+        elif transport == "exchange":
+            self._buf = [torch.zeros((self.rows, nx), dtype=torch.float64, device=self.device) for _ in range(2)]
+            self._cur = 0
+            self._coef = torch.from_numpy(coef).to(self.device)
+            self.st = api.Stencil2D(variant, nx, self.rows, self._buf[1], self._buf[0], self._coef, deviceNum=dev, H=H, L=L,
+                                    R=R, V=V, T=T, B=B, fun=fun, numCoe=numCoe, numTiles=numTiles)
+            if not self.is_x:
+                self.top = torch.empty((max(self.T, 1), nx), dtype=torch.float64, device=self.device)
+                self.bottom = torch.empty((max(self.B, 1), nx), dtype=torch.float64, device=self.device)
+                self.st.set_slab(self.top, self.bottom, self.rank == 0, self.rank == self.world - 1)
         else:
             raise ValueError(transport)
 
+    # ---- buffers ---------------------------------------------------------------------------------------------------
+    def _field(self, which):
+        if self.slab:
+            return device_view(self.lib.custen_slab_field(self.slab, which), (self.rows, self.nx), self.device)
+        return self._buf[self._cur ^ which]
+
+    @property
+    def input(self):
+        return self._field(0)
+
+    @property
+    def output(self):
+        return self._field(1)
+
+    # ---- stepping --------------------------------------------------------------------------------------------------
     def step(self):
         """One sweep over the global grid (this rank's share), halos included."""
+        if self.slab:
+            self.lib.custen_slab_compute(self.slab)
+            return
         if not self.is_x and (self.T or self.B):
-            if self.transport == "exchange" or self.world == 1:
-                exchange_halos(self.inp, self.T, self.B, self.top[: self.T], self.bottom[: self.B], self.rank,
-                               self.world, self.periodic, self.group)
-            else:
-                # peer transport: the sweep reads the neighbours' edge rows in place, so all a step needs is to
-                # know that the neighbours have finished the previous one (and are done reading my rows)
-                from . import _lib
-                self._epoch += 1
-                _lib.load().custen_peer_barrier(ctypes.addressof(self.st.handle), self._up_flags, self._down_flags,
-                                                self._flags, self._epoch)
+            exchange_halos(self.input, self.T, self.B, self.top[: self.T], self.bottom[: self.B], self.rank, self.world,
+                           self.periodic, self.group)
         self.st.compute(0)
 
+    def swap(self):
+        if self.slab:
+            self.lib.custen_slab_swap(self.slab)
+            return
+        self.st.swap(self._buf[self._cur ^ 1])
+        self._cur ^= 1
+
+    def run(self, nsteps):
+        """nsteps x (sweep + swap); the peer transport replays pairs of steps from a CUDA graph."""
+        if self.slab:
+            self.lib.custen_slab_run(self.slab, nsteps)
+            return
+        for _ in range(nsteps):
+            self.step()
+            self.swap()
+
+    def synchronize(self):
+        if self.slab:
+            self.lib.custen_slab_synchronize(self.slab)
+        else:
+            torch.cuda.synchronize()
+
+    @property
+    def path(self):
+        from .api import PATH_NAMES
+        if self.slab:
+            return PATH_NAMES.get(self.lib.custen_slab_last_path(self.slab), "?")
+        return self.st.path
+
+    def error(self):
+        return bool(self.slab and self.lib.custen_slab_error(self.slab))
+
     def destroy(self):
-        from . import _lib
-        from .api import device_synchronize
-        device_synchronize()
+        torch.cuda.synchronize()
         if dist.is_initialized() and self.world > 1:
             dist.barrier(group=self.group)  # nobody unmaps memory a neighbour may still be reading
-        self.st.destroy()
-        for p in self._mapped:
-            _lib.load().custen_ipc_close(p)
-        self._mapped = []
-        if getattr(self, "_flags", None):
-            _lib.load().custen_device_free(self._flags)
-            self._flags = None
+        if self.slab:
+            self.lib.custen_slab_destroy(self.slab)
+            self.slab = None
+        elif getattr(self, "st", None):
+            self.st.destroy()
+            self.st = None

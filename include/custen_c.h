@@ -98,6 +98,11 @@ void custen_set_tuning(int force_fallback, int force_tile, int chunk_rows, int c
  * grid in place over the host link (preferred location CPU + accessed-by advice) instead of migrating every tile both
  * ways.  1: always the reference's prefetch pipeline. */
 void custen_set_managed_policy(int policy);
+/* The same for one handle only (-1: follow the process-wide setting again). */
+void custen_set_handle_managed_policy(cuSten_c_handle* pt_cuSten, int policy);
+/* cudaMemAdvise / cudaMemPrefetchAsync (legacy stream) for FFI callers; return the cudaError_t. device -1 = the CPU. */
+int custen_mem_advise(const void* p, size_t bytes, int advice, int device);
+int custen_mem_prefetch(const void* p, size_t bytes, int device);
 
 /* Multi-GPU y-slab layer: the handle's grid is one slab of a taller global grid.  `top` / `bottom` point at the
  * numStenTop rows above / numStenBottom rows below the slab (a local halo buffer filled by an exchange, or a
@@ -138,8 +143,64 @@ void custen_event_destroy(void* ev);
  * examples/src/2d_x_p.cu:73-75). */
 void* custen_host_alloc(size_t bytes);
 void custen_host_free(void* p);
+/* Pinned host memory bound to the NUMA node of `device` (mmap + mbind + cudaHostRegister); *node_out = that node, or -1
+ * when binding was not possible.  custen_link_probe: plain cudaMemcpyAsync both ways at once over those buffers, ms. */
+int custen_device_numa_node(int device);
+void* custen_host_alloc_near(size_t bytes, int device, int* node_out);
+void custen_host_free_near(void* p, size_t bytes);
+float custen_link_probe(const void* host_src, void* host_dst, size_t bytes, int iters, int device);
 void* custen_managed_alloc(size_t bytes);
 void custen_managed_free(void* p);
+
+/* ---- Multi-GPU y-slab layer with time stepping (custen_b200/csrc/slab.cu; new, no reference counterpart) ----------
+ * A slab owns rows [rank ny/world, (rank+1) ny/world) of BOTH field buffers of a global ny x nx grid; the halo rows of
+ * a sweep are read in place from the neighbour GPUs' memory - the reference's boundaryTop / boundaryBottom kernel
+ * arguments (cuSten/src/kernels/2d_xy_p_kernel.cu:67-68) pointed at peer memory - and custen_slab_swap re-aliases input,
+ * output and seams like cuStenSwap2D* (cuSten/src/struct/custenCreateDestroy2DXYp.cu:253-310).  The neighbour wait is
+ * inside the sweep kernel (only the work items that touch halo rows wait; the last CTA publishes the slab's sweep
+ * count), so a step is one launch and steps replay from a CUDA graph.
+ * variant: index into Xp Xnp XpFun XnpFun Yp Ynp YpFun YnpFun XYp XYnp XYpFun XYnpFun; coef_host: ncoef doubles
+ * (weights, or the function's coefficients) in host memory; func: device function pointer for the Fun variants, valid
+ * on `device` (custen_builtin_fun, or cudaMemcpyFromSymbol in the caller).
+ * One process per GPU: create -> export (64-byte IPC handle + offset, moved by the caller) -> connect (NULL where the
+ * slab touches a physical edge of a non-periodic grid) -> [fill custen_slab_field(.,0)] -> host barrier -> run. */
+void* custen_slab_create(int variant, int device, int rank, int world, int nx, int ny_global, const double* coef_host,
+                         int ncoef, int H, int L, int R, int V, int T, int B, double* func);
+void custen_slab_export(void* slab, void* handle64, size_t* offset_out);
+void custen_slab_connect(void* slab, const void* up_handle64, size_t up_offset, const void* down_handle64, size_t down_offset);
+double* custen_slab_field(void* slab, int which);      /* 0: input of the next sweep (= latest result), 1: its output */
+int custen_slab_rows(void* slab);
+void custen_slab_compute(void* slab);                   /* one sweep, asynchronous */
+void custen_slab_swap(void* slab);
+void custen_slab_run(void* slab, int nsteps);           /* nsteps x (compute + swap), pairs replayed from a CUDA graph */
+void custen_slab_run_plain(void* slab, int nsteps);     /* the same, launch by launch */
+float custen_slab_time_run(void* slab, int nsteps);     /* milliseconds (CUDA events on the slab's stream); synchronises */
+void custen_slab_synchronize(void* slab);
+int custen_slab_error(void* slab);                      /* 1: a neighbour wait timed out */
+void custen_slab_set_timeout(void* slab, double seconds); /* default 20 s; 0 = wait for ever */
+int custen_slab_last_path(void* slab);
+void custen_slab_destroy(void* slab);
+
+/* The same layer for ONE process driving several GPUs (what an existing single-process cuSten program can call;
+ * SURVEY.md section 7 step 5).  devices[i] carries slab i; peers are reached with cudaDeviceEnablePeerAccess.  A device may
+ * appear more than once (its slabs then share a stream and run in rank order) - the layout the one-GPU tests use.
+ * builtin_fun names one of the library's fixtures, else funcs[i] is the user function's address on devices[i]. */
+void* custen_mg_create(int ndev, const int* devices, int variant, int nx, int ny, const double* coef_host, int ncoef, int H,
+                       int L, int R, int V, int T, int B, const char* builtin_fun, double* const* funcs);
+void custen_mg_scatter(void* mg, const double* host_field);          /* ny x nx -> the slabs' current input */
+void custen_mg_gather(void* mg, double* host_field, int which);      /* synchronises; which as custen_slab_field */
+void custen_mg_fill_output(void* mg, double value);
+void custen_mg_compute(void* mg);
+void custen_mg_swap(void* mg);
+void custen_mg_run(void* mg, int nsteps);
+void custen_mg_synchronize(void* mg);
+int custen_mg_error(void* mg);
+void* custen_mg_slab(void* mg, int i);
+void custen_mg_destroy(void* mg);
+
+/* Synthetic input, regenerable anywhere: field[r][c] = lo + (hi - lo) * u(seed, (row0 + r) * nx + c), u = the top 53
+ * bits of splitmix64(seed + index) / 2^53 (tests/cases.py hash_field is the numpy twin).  Legacy stream. */
+void custen_fill_hash(double* dev_field, long long row0, int rows, int nx, unsigned long long seed, double lo, double hi);
 
 /* Cahn-Hilliard ADI solver re-hosted on the engine (reference program cuPentCahnADI/src/cuPentCahnADI.cu and its
  * timing twin cuPentSpeedUp/cuPentCahnADITiming/src/cuPentCahnADI.cu, whose main() this replaces):

@@ -62,6 +62,19 @@ def field(kind, nx, ny, seed=0x5EED):
     raise ValueError(kind)
 
 
+def hash_field(row0, rows, nx, seed, lo, hi):
+    """numpy twin of custen_fill_hash (custen_b200/csrc/api_c.cu): rows [row0, row0 + rows) of the synthetic field whose
+    point (r, c) is lo + (hi - lo) * u(seed, r * nx + c), u = top 53 bits of splitmix64's finaliser / 2^53."""
+    idx = (np.uint64(row0) * np.uint64(nx) + np.arange(rows * nx, dtype=np.uint64))
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed) + idx * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    u = (z >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+    return (lo + (hi - lo) * u).reshape(rows, nx)
+
+
 def _c(name, variant, nx, ny, tiles, block, coef, H=1, L=0, R=0, V=1, T=0, B=0, fun=None, numCoe=None, fld="random"):
     return dict(name=name, variant=variant, nx=nx, ny=ny, tiles=tiles, block=block, coef=np.asarray(coef, float),
                 H=H, L=L, R=R, V=V, T=T, B=B, fun=fun, numCoe=numCoe, field=fld)

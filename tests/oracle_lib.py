@@ -66,6 +66,32 @@ def oracle_sweep(variant, inp, out, coef, H=1, L=0, R=0, V=1, T=0, B=0, fun=None
     return out
 
 
+def oracle_time_steps(variant, in0, out0, coef, steps, **kw):
+    """`steps` x (Compute + Swap) on a whole grid, the way a cuSten caller time-steps (the output buffer of one step is
+    the input of the next and vice versa; regions a variant does not write keep what the buffer held).  Returns
+    (latest result, the other buffer)."""
+    a = np.ascontiguousarray(in0, dtype=np.float64).copy()
+    b = np.ascontiguousarray(out0, dtype=np.float64).copy()
+    for _ in range(steps):
+        oracle_sweep(variant, a, b, coef, **kw)
+        a, b = b, a
+    return a, b
+
+
+def oracle_evolve_band(variant, band0, coef, steps, T, B, **kw):
+    """Time-step a horizontal band of a y-periodic grid without its neighbours: x wraps, y does not, so every step
+    eats T rows at the top and B at the bottom.  Returns (band after `steps` steps, first valid row, end valid row);
+    rows outside [first, end) are garbage.  Used to check a few rows of a grid too large for a whole-grid oracle."""
+    d, periodic, is_fun = variant_parts(variant)
+    assert periodic
+    a = np.ascontiguousarray(band0, dtype=np.float64).copy()
+    b = np.zeros_like(a)
+    for _ in range(steps):
+        oracle_sweep(variant, a, b, coef, T=T, B=B, periodic_bits=1, **kw)
+        a, b = b, a
+    return a, steps * T, a.shape[0] - steps * B
+
+
 _serial = None
 
 
