@@ -80,6 +80,7 @@ int launch_band(const Band& band, cudaStream_t stream);
 
 // Counters (process-wide, relaxed): kernels launched by this library.
 uint64_t launches_total();
+void launches_add(uint64_t n);   // kernels replayed from a captured graph
 
 }  // namespace custen
 

@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(FB_BX* FB_BY) fallback_kernel(const __grid_con
 
 static std::atomic<uint64_t> g_launches{0};
 uint64_t launches_total() { return g_launches.load(std::memory_order_relaxed); }
+void launches_add(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 Tuning& tuning()
 {
@@ -206,7 +207,15 @@ static void resolve_occupancy(const void* kernel, int threads, size_t& smem, int
         }
     }
     const size_t smem_in = smem;
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // the opt-in is one number per (kernel, device): it only ever grows, so that every remembered request stays launchable
+    size_t opted = 0;
+    for (int i = 0; i < n; ++i)
+        if (g_memo[i].kernel == kernel && g_memo[i].device == dev && g_memo[i].smem_out > opted) opted = g_memo[i].smem_out;
+    if (smem > opted)
+    {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        opted = smem;
+    }
     cps = tuned;
     if (cps <= 0)
     {
@@ -222,7 +231,7 @@ static void resolve_occupancy(const void* kernel, int threads, size_t& smem, int
         if (smem < need && (need + per_cta_reserved) * (size_t)cps <= sm_bytes && need <= 227 * 1024)
         {
             smem = need;
-            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (smem > opted) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         }
     }
     while (g_memo_lock.test_and_set(std::memory_order_acquire)) {}

@@ -520,7 +520,10 @@ static void compute_managed(cuSten_t* h, Plan* p, const double* coef, MemKind kc
     {
         if (left_at(p, sp, nsp, 1))
         {
-            if (kcoef == MK_MANAGED) prefetch(coef, (size_t)p->ncoef * sizeof(double), dev, h->streams[0]);
+            // the coefficients came over with the call that brought the grid; a prefetch that moves nothing still costs
+            // a few hundred microseconds of stream time, so it is not repeated (pages the CPU rewrote fault back in)
+            if (kcoef == MK_MANAGED && p->coef_on_gpu != coef) prefetch(coef, (size_t)p->ncoef * sizeof(double), dev, h->streams[0]);
+            p->coef_on_gpu = coef;
             compute_resident(h, p, coef);
             p->last_mode = 4;
             return;
@@ -558,7 +561,8 @@ static void compute_managed(cuSten_t* h, Plan* p, const double* coef, MemKind kc
             }
             if (ok)
             {
-                    if (kcoef == MK_MANAGED) prefetch(coef, (size_t)p->ncoef * sizeof(double), dev, h->streams[0]);
+                    if (kcoef == MK_MANAGED && p->coef_on_gpu != coef) prefetch(coef, (size_t)p->ncoef * sizeof(double), dev, h->streams[0]);
+                p->coef_on_gpu = coef;
                 cudaStream_t st = h->streams[0];
                 compute_resident(h, p, coef);
                 p->last_mode = 5;
@@ -584,6 +588,7 @@ static void compute_managed(cuSten_t* h, Plan* p, const double* coef, MemKind kc
     p->res_where = 0;
     if (spans_complete && !offload) note_left_at(p, sp, nsp, 1);  // the pipeline below leaves every tile on the GPU
     if (kcoef == MK_MANAGED) prefetch(coef, (size_t)p->ncoef * sizeof(double), dev, h->streams[1]);
+    p->coef_on_gpu = kcoef == MK_MANAGED ? coef : nullptr;
     prefetch_tile(h, 0, dev, h->streams[1]);
     cudaEventRecord(h->events[0], h->streams[1]);
     for (int t = 0; t < h->numTiles; ++t)

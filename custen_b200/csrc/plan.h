@@ -42,6 +42,7 @@ struct Plan
     const void* res_ptr[kMaxSpans];
     size_t res_bytes[kMaxSpans];
     int res_n, res_where;
+    const double* coef_on_gpu;   // unified-memory coefficients this handle has already prefetched to the GPU
     // slab extension (multi-GPU layer): rows above / below the grid come from these buffers
     const double* slab_top;
     const double* slab_bottom;

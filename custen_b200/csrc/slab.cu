@@ -184,7 +184,8 @@ bool slab_graph(Slab* s)
         slab_swap(s);
     }
     const cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
-    s->sweeps = sweeps0;   // nothing ran: capture only records
+    launches_add((uint64_t)-2);   // nothing ran: capture only records
+    s->sweeps = sweeps0;
     if (s->cur != cur0) slab_swap(s);
     if (e != cudaSuccess || !graph || cudaGraphInstantiate(&s->gexec, graph, 0) != cudaSuccess)
     {
@@ -208,6 +209,7 @@ void slab_run(Slab* s, int nsteps, bool use_graph)
         if (use_graph && s->sweeps > 0 && it + 1 < nsteps && slab_graph(s) && s->cur == s->gexec_cur)
         {
             cudaGraphLaunch(s->gexec, s->stream);
+            launches_add(2);
             s->sweeps += 2;
             ++it;
             continue;

@@ -30,9 +30,14 @@ def main():
     coef, kw = bench.stencil_args(variant, n)
     cnt = n * n
     for first_touch in ("cpu", "gpu"):
-        for prep in ("none", "advise_pref_gpu", "prefetch_whole", "advise+prefetch", "rehome_via_cpu", "policy_pipeline"):
+        for prep in ("none", "coef_in_device_memory", "advise_pref_gpu", "prefetch_whole", "policy_pipeline"):
             m_in, m_out, m_w = lib.custen_managed_alloc(cnt * 8), lib.custen_managed_alloc(cnt * 8), lib.custen_managed_alloc(9 * 8)
             np.ctypeslib.as_array((ctypes.c_double * 9).from_address(m_w))[:] = coef
+            w_arg = m_w
+            if prep == "coef_in_device_memory":
+                import torch
+                w_dev = torch.from_numpy(coef).cuda()
+                w_arg = w_dev
             if prep in ("advise_pref_gpu", "advise+prefetch"):
                 for p in (m_in, m_out):
                     lib.custen_mem_advise(p, cnt * 8, ADV_SET_PREF, 0)
@@ -63,7 +68,7 @@ def main():
                 cs.device_synchronize()
             t_prep = time.perf_counter() - t0
             cs.set_managed_policy(1 if prep == "policy_pipeline" else 0)
-            st = cs.Stencil2D(variant, n, n, m_out, m_in, m_w, numTiles=tiles, **kw)
+            st = cs.Stencil2D(variant, n, n, m_out, m_in, w_arg, numTiles=tiles, **kw)
             t0 = time.perf_counter()
             st.compute(cs.DEVICE)
             cs.device_synchronize()
