@@ -48,7 +48,8 @@ EXPORTED = (
        "custen_slab_synchronize", "custen_slab_error", "custen_slab_set_timeout", "custen_slab_last_path",
        "custen_slab_destroy", "custen_mg_create", "custen_mg_scatter", "custen_mg_gather", "custen_mg_fill_output",
        "custen_mg_compute", "custen_mg_swap", "custen_mg_run", "custen_mg_synchronize", "custen_mg_error", "custen_mg_slab",
-       "custen_mg_destroy", "custen_device_numa_node", "custen_host_alloc_near", "custen_host_free_near", "custen_link_probe"]
+       "custen_mg_destroy", "custen_device_numa_node", "custen_host_alloc_near", "custen_host_free_near", "custen_link_probe",
+       "custen_cahn_set_partition_rows", "custen_cahn_config", "custen_pent_part_host", "custen_pent_part_choose_np"]
 )
 
 _lib = None
@@ -162,6 +163,10 @@ def load():
     lib.custen_host_free_near.argtypes, lib.custen_host_free_near.restype = [_c_void_p, ctypes.c_size_t], None
     lib.custen_link_probe.argtypes = [_c_void_p, _c_void_p, ctypes.c_size_t, _c_int, _c_int]
     lib.custen_link_probe.restype = ctypes.c_float
+    lib.custen_cahn_set_partition_rows.argtypes, lib.custen_cahn_set_partition_rows.restype = [_c_int], None
+    lib.custen_cahn_config.argtypes, lib.custen_cahn_config.restype = [_c_void_p, _c_int, _c_int], _c_int
+    lib.custen_pent_part_host.argtypes, lib.custen_pent_part_host.restype = [_c_int, _c_int, _c_void_p, _c_void_p, _c_void_p], _c_int
+    lib.custen_pent_part_choose_np.argtypes, lib.custen_pent_part_choose_np.restype = [_c_int, _c_int], _c_int
     _lib = lib
     return lib
 

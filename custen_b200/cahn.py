@@ -11,10 +11,22 @@ class CahnHilliard:
     """2D Cahn-Hilliard, periodic n x n grid of side lx, dt = dt_over_dx * lx / n (reference: D = 1, gamma = 0.01,
     dt_over_dx = 0.1; lx = 2 pi in the demo, 16 pi in the timing twins)."""
 
-    def __init__(self, n, D=1.0, gamma=0.01, lx=16.0 * math.pi, dt_over_dx=0.1, device=0):
+    def __init__(self, n, D=1.0, gamma=0.01, lx=16.0 * math.pi, dt_over_dx=0.1, device=0, solver=None, fused=None,
+                 graph=None):
+        """solver: 2 partitioned tolerance-mode pentadiagonal solve (default; within 1e-13 of the reference's solver),
+        0 / 1 the two solves that keep the reference's operation order (bit-identical results).  fused / graph: see
+        include/custen_c.h.  None leaves the library default (custen_cahn_set_*)."""
         self.lib = _lib.load()
         self.n = n
         self.h = self.lib.custen_cahn_create(n, D, gamma, lx, dt_over_dx, device)
+        for key, value in ((0, solver), (1, fused), (2, graph)):
+            if value is not None:
+                self.lib.custen_cahn_config(self.h, key, int(value))
+
+    @property
+    def solver(self):
+        """The pentadiagonal solve in force (2 falls back to 0 where the partitioned layout cannot take the grid)."""
+        return self.lib.custen_cahn_config(self.h, 0, -1)
 
     def set_field(self, c0):
         c0 = np.ascontiguousarray(c0, dtype=np.float64)

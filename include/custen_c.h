@@ -214,7 +214,19 @@ float custen_cahn_time_steps(void* solver, int nsteps);         /* milliseconds 
 void custen_cahn_destroy(void* solver);
 void custen_cahn_set_fused(int on);                             /* 1: fused right-hand-side pass (default), 0: via cuStenCompute2D* */
 void custen_cahn_set_graph(int on);                             /* 1: replay the fused step from a CUDA graph (default), 0: kernel by kernel */
-void custen_cahn_set_solver(int which);                         /* 0: TMA-fed pentadiagonal solve (default), 1: cp.async ring version */
+/* The custen_cahn_set_* switches are the defaults for solvers created AFTERWARDS; every solver keeps its own copy
+ * (custen_cahn_config changes one solver).
+ * solver 2 (default): partitioned tolerance-mode solve (custen_b200/csrc/pent_part.cu) - within 1e-13 of the reference's
+ * solver (cuPentBatch.cu:119-198 + BatchHyper.cu:195-259), not bit-identical; falls back to 0 where the layout cannot
+ * take it (n % 32 != 0).  0: TMA-fed solve in the reference's operation order (bit-identical), 1: its cp.async twin. */
+void custen_cahn_set_solver(int which);
+void custen_cahn_set_partition_rows(int np);                    /* rows per partition of solver 2: 32 .. 256, multiple of 32 (default 128) */
+int custen_cahn_config(void* solver, int key, int value);       /* key 0 solver, 1 fused, 2 graph, 3 table rows; value < 0 queries */
+/* The partitioned algorithm's arithmetic on the host for ONE periodic pentadiagonal system (diagonals coef5 = a b c d e
+ * at offsets -2 .. +2): pins tables and algorithm against a dense solve without a GPU.  Returns the number of
+ * interface coupling blocks kept, 0 if (n, np) is not a valid partitioning. */
+int custen_pent_part_host(int n, int np, const double* coef5, const double* rhs, double* x);
+int custen_pent_part_choose_np(int n, int wanted);
 void custen_cahn_set_table_rows(int rows);                      /* tuning / tests: coefficient rows staged per refill */
 
 /* The same solver on one y-slab of the grid (one process per GPU; BASELINE.json config 5 at 2-8 GPUs), driven phase by

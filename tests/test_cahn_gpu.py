@@ -22,21 +22,15 @@ def _initial(n, seed=0):
     return np.random.default_rng(seed).uniform(-0.1, 0.1, size=(n, n))
 
 
-def _ours(c0, nsteps, lx=LX, solver=0, fused=1):
-    """solver 0: the TMA-fed pentadiagonal solve (default), 1: the cp.async ring version.
+def _ours(c0, nsteps, lx=LX, solver=0, fused=1, graph=None):
+    """solver 0: the TMA-fed pentadiagonal solve in the reference's operation order, 1: its cp.async ring version,
+    2: the partitioned tolerance-mode solve (the library default).
     fused 1: right-hand side in one pass (default), 0: findCBar + cuStenCompute2DXYp / XYpFun + findRHS."""
-    import custen_b200 as cs
-    cs.load().custen_cahn_set_solver(solver)
-    cs.load().custen_cahn_set_fused(fused)
-    try:
-        s = CahnHilliard(c0.shape[0], lx=lx)
-        s.set_field(c0)
-        s.step(nsteps)
-        out = s.field()
-        s.destroy()
-    finally:
-        cs.load().custen_cahn_set_solver(0)
-        cs.load().custen_cahn_set_fused(1)
+    s = CahnHilliard(c0.shape[0], lx=lx, solver=solver, fused=fused, graph=graph)
+    s.set_field(c0)
+    s.step(nsteps)
+    out = s.field()
+    s.destroy()
     return out
 
 
@@ -66,20 +60,22 @@ def test_against_reference_serial_cpu_twin(n, steps):
     assert rel < 1e-11, rel
 
 
-def test_mass_is_conserved_at_full_size():
+@pytest.mark.parametrize("solver", [0, 2])
+def test_mass_is_conserved_at_full_size(solver):
     """Size-independent property at the BASELINE size (4096^2): the scheme conserves the mean of c."""
     n = 4096
     c0 = _initial(n, seed=1)
-    got = _ours(c0, 10)
+    got = _ours(c0, 10, solver=solver)
     assert np.isfinite(got).all()
     assert abs(got.mean() - c0.mean()) < 1e-13
     assert 0.0 < np.abs(got).max() < 0.2
 
 
-def test_steps_compose():
+@pytest.mark.parametrize("solver", [0, 2])
+def test_steps_compose(solver):
     c0 = _initial(128, seed=3)
-    a = _ours(c0, 12)
-    s = CahnHilliard(128)
+    a = _ours(c0, 12, solver=solver)
+    s = CahnHilliard(128, solver=solver)
     s.set_field(c0)
     for _ in range(4):
         s.step(3)
@@ -140,20 +136,16 @@ def test_fused_right_hand_side_matches_the_engine_path(n):
     assert ol.count_diff(a, b) == 0
 
 
+@pytest.mark.parametrize("solver", [0, 2])
 @pytest.mark.parametrize("n,steps", [(128, 1), (128, 2), (256, 7), (512, 12)])
-def test_graph_replay_matches_kernel_by_kernel(n, steps):
+def test_graph_replay_matches_kernel_by_kernel(n, steps, solver):
     """The fused step replayed from a CUDA graph (pairs of steps; the first step and an odd last one run kernel by
     kernel) against plain launches, also when steps are requested in several calls."""
-    import custen_b200 as cs
     c0 = _initial(n, seed=3 * n + steps)
-    cs.load().custen_cahn_set_graph(0)
-    try:
-        want = _ours(c0, steps)
-    finally:
-        cs.load().custen_cahn_set_graph(1)
-    got = _ours(c0, steps)
+    want = _ours(c0, steps, solver=solver, graph=0)
+    got = _ours(c0, steps, solver=solver)
     assert ol.count_diff(got, want) == 0
-    s = CahnHilliard(n, lx=LX)
+    s = CahnHilliard(n, lx=LX, solver=solver)
     s.set_field(c0)
     done = 0
     for chunk in (1, 3, 2, 5, 1):
@@ -166,3 +158,81 @@ def test_graph_replay_matches_kernel_by_kernel(n, steps):
     split = s.field()
     s.destroy()
     assert ol.count_diff(split, want) == 0
+
+
+# ---- the partitioned tolerance-mode solve (solver 2, the default): BASELINE.json north_star allows 1e-13 relative --------
+
+def _rel(got, want):
+    return np.max(np.abs(got - want)) / np.max(np.abs(want))
+
+
+@pytest.mark.parametrize("n,steps", [(64, 5), (96, 8), (256, 25), (512, 100), (1024, 10)])
+def test_partitioned_solve_within_tolerance_of_reference_gpu_solver(n, steps):
+    """max|c - c_ref| / max|c_ref| <= 1e-13 after `steps` time steps against the reference's own GPU solver
+    (cuPentCahnADITiming + BatchHyper + cuPentBatch rebuilt for sm_100), 100 steps at the reference's 512^2."""
+    c0 = _initial(n, seed=n + 1)
+    ref = ol.ref_cahn_run(c0, steps, LX)
+    if ref is None:
+        pytest.skip("reference GPU solver not built")
+    s = CahnHilliard(n, lx=LX, solver=2)
+    assert s.solver == 2
+    s.set_field(c0)
+    s.step(steps)
+    got = s.field()
+    s.destroy()
+    assert _rel(got, ref[0]) <= 1e-13, _rel(got, ref[0])
+
+
+@pytest.mark.parametrize("np_rows", [32, 64, 128, 256])
+def test_partition_height_does_not_matter(np_rows):
+    import custen_b200 as cs
+    c0 = _initial(512, seed=77)
+    want = _ours(c0, 10, solver=0)
+    cs.load().custen_cahn_set_partition_rows(np_rows)
+    try:
+        got = _ours(c0, 10, solver=2)
+    finally:
+        cs.load().custen_cahn_set_partition_rows(128)
+    assert _rel(got, want) <= 1e-13
+
+
+def test_partitioned_solve_falls_back_where_the_layout_cannot_take_it():
+    s = CahnHilliard(100, solver=2)
+    assert s.solver == 0
+    c0 = _initial(100, seed=4)
+    s.set_field(c0)
+    s.step(4)
+    got = s.field()
+    s.destroy()
+    assert ol.count_diff(got, _ours(c0, 4, solver=0)) == 0
+
+
+def test_config5_full_size_against_reference_gpu_solver():
+    """BASELINE.json config 5 at its own size, 4096^2, 3 steps: the bit-identical road has 0 differing points, the
+    default tolerance-mode road is within 1e-13."""
+    n, steps = 4096, 3
+    c0 = _initial(n, seed=11)
+    ref = ol.ref_cahn_run(c0, steps, LX)
+    if ref is None:
+        pytest.skip("reference GPU solver not built")
+    exact = _ours(c0, steps, solver=0)
+    assert ol.count_diff(exact, ref[0]) == 0
+    tol = _ours(c0, steps, solver=2)
+    assert _rel(tol, ref[0]) <= 1e-13, _rel(tol, ref[0])
+
+
+def test_two_solvers_in_one_process_keep_their_own_switches():
+    c0 = _initial(256, seed=8)
+    a = CahnHilliard(256, solver=0)
+    b = CahnHilliard(256, solver=2)
+    a.set_field(c0)
+    b.set_field(c0)
+    for _ in range(3):
+        a.step(2)
+        b.step(2)
+    fa, fb = a.field(), b.field()
+    a.destroy()
+    b.destroy()
+    assert ol.count_diff(fa, _ours(c0, 6, solver=0)) == 0
+    assert ol.count_diff(fb, _ours(c0, 6, solver=2)) == 0
+    assert _rel(fb, fa) <= 1e-13

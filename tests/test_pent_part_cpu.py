@@ -1,0 +1,105 @@
+"""The partitioned ("tolerance mode") cyclic pentadiagonal solve, custen_b200/csrc/pent_part.cu: its tables and its
+arithmetic - restated on the host operation for operation by custen_pent_part_host, no GPU involved - against a dense
+solve of the same periodic system.  The systems are the ones the Cahn-Hilliard ADI step solves
+(/root/reference/cuPentCahnADI/src/cuPentCahnADI.cu:389-395: a = e = sigma, b = d = -4 sigma, c = 1 + 6 sigma);
+BASELINE.json's north_star tolerance, 1e-13 relative, is the bar."""
+import ctypes
+import math
+
+import numpy as np
+import pytest
+
+import custen_b200 as cs
+
+
+def _sigma(n, lx=16.0 * math.pi, D=1.0, gamma=0.01, dt_over_dx=0.1):
+    dx = lx / n
+    dt = dt_over_dx * dx
+    return 2.0 * dt * D * gamma / (3.0 * dx ** 4)
+
+
+def _coef(sig):
+    return np.array([sig, -4 * sig, 1 + 6 * sig, -4 * sig, sig])
+
+
+def _circulant_solve(co, rhs):
+    """Reference answer in extended precision: the matrix is circulant and SPD, so its eigenvalues are
+    1 + sigma (2 cos t - 2)^2; solve in the Fourier basis with long doubles via a dense solve for small n and
+    iterative refinement of an FFT solve for large n."""
+    n = rhs.shape[0]
+    if n <= 1024:
+        A = np.zeros((n, n), dtype=np.longdouble)
+        for k, off in enumerate((-2, -1, 0, 1, 2)):
+            for i in range(n):
+                A[i, (i + off) % n] += co[k]
+        # numpy has no long-double solver: solve in double, refine the residual in long double
+        Ad = A.astype(np.float64)
+        x = np.linalg.solve(Ad, rhs).astype(np.longdouble)
+        for _ in range(3):
+            r = rhs.astype(np.longdouble) - A @ x
+            x = x + np.linalg.solve(Ad, r.astype(np.float64)).astype(np.longdouble)
+        return x.astype(np.float64)
+    t = 2.0 * np.pi * np.arange(n) / n
+    lam = co[2] + 2 * co[1] * np.cos(t) + 2 * co[0] * np.cos(2 * t)
+
+    def apply(x):
+        x = x.astype(np.longdouble)
+        return (co[0] * np.roll(x, 2) + co[1] * np.roll(x, 1) + co[2] * x + co[3] * np.roll(x, -1) + co[4] * np.roll(x, -2))
+
+    x = np.real(np.fft.ifft(np.fft.fft(rhs) / lam)).astype(np.longdouble)
+    for _ in range(3):
+        r = (rhs.astype(np.longdouble) - apply(x)).astype(np.float64)
+        x = x + np.real(np.fft.ifft(np.fft.fft(r) / lam)).astype(np.longdouble)
+    return x.astype(np.float64)
+
+
+def _part_host(n, npart, co, rhs):
+    lib = cs.load()
+    x = np.empty(n)
+    nb = lib.custen_pent_part_host(n, npart, co.ctypes.data, rhs.ctypes.data, x.ctypes.data)
+    return nb, x
+
+
+@pytest.mark.parametrize("n,npart", [(64, 32), (128, 32), (128, 64), (256, 128), (512, 128), (512, 256), (1024, 64),
+                                     (4096, 128), (4096, 256), (4096, 32)])
+def test_partitioned_solve_matches_dense_solve(n, npart):
+    co = _coef(_sigma(n))
+    rng = np.random.default_rng(n + npart)
+    for trial in range(3):
+        rhs = rng.uniform(-1.0, 1.0, n) if trial else np.cos(2 * np.pi * np.arange(n) / n) + 0.3
+        nb, x = _part_host(n, npart, co, rhs)
+        assert nb >= 1
+        want = _circulant_solve(co, rhs)
+        rel = np.max(np.abs(x - want)) / np.max(np.abs(want))
+        assert rel < 1e-13, (n, npart, trial, rel)
+
+
+@pytest.mark.parametrize("sig", [1e-3, 0.05, 1.0, 30.0, 1e3])
+def test_other_stiffnesses(sig):
+    """sigma far from the Cahn-Hilliard value: the spikes decay slower as sigma grows, more coupling blocks are kept,
+    the answer stays within the tolerance scaled by the system's condition number (1 + 16 sigma)."""
+    n, npart = 512, 64
+    co = _coef(sig)
+    rhs = np.random.default_rng(5).uniform(-1.0, 1.0, n)
+    nb, x = _part_host(n, npart, co, rhs)
+    assert nb >= 1
+    want = _circulant_solve(co, rhs)
+    rel = np.max(np.abs(x - want)) / np.max(np.abs(want))
+    assert rel < 1e-13 * max(1.0, 1 + 16 * sig), (sig, nb, rel)
+
+
+def test_invalid_partitionings_are_refused():
+    co = _coef(0.1)
+    rhs = np.ones(100)
+    assert _part_host(100, 32, co, rhs)[0] == 0     # 100 % 32 != 0
+    assert _part_host(64, 64, co, np.ones(64))[0] == 0   # a single partition has no ring
+
+
+def test_choose_np():
+    lib = cs.load()
+    assert lib.custen_pent_part_choose_np(4096, 128) == 128
+    assert lib.custen_pent_part_choose_np(4096, 256) == 256
+    assert lib.custen_pent_part_choose_np(96, 128) == 32
+    assert lib.custen_pent_part_choose_np(64, 128) == 32
+    assert lib.custen_pent_part_choose_np(100, 128) == 0
+    assert lib.custen_pent_part_choose_np(32, 128) == 0
