@@ -10,7 +10,7 @@ OBJDIR    := build/obj
 LIBDIR    := custen_b200/lib
 
 CORE_SRC  := kernels.cu plan.cu api_cpp.cu
-CABI_SRC  := api_c.cu slab.cu cahn.cu pent_tma.cu pent_part.cu
+CABI_SRC  := api_c.cu slab.cu cahn.cu cahn_part.cu pent_tma.cu pent_part.cu
 CORE_OBJ  := $(patsubst %.cu,$(OBJDIR)/%.o,$(CORE_SRC))
 CABI_OBJ  := $(patsubst %.cu,$(OBJDIR)/%.o,$(CABI_SRC))
 HEADERS   := $(wildcard $(SRCDIR)/*.h $(SRCDIR)/*.cuh include/*.h)

@@ -40,8 +40,12 @@ EXPORTED = (
        "custen_host_free", "custen_managed_alloc", "custen_managed_free", "custen_peer_barrier", "custen_device_alloc",
        "custen_device_free", "custen_cahn_create", "custen_cahn_set_field", "custen_cahn_step", "custen_cahn_get_field",
        "custen_cahn_time_steps", "custen_cahn_destroy", "custen_cahn_set_table_rows", "custen_cahn_set_solver", "custen_cahn_set_fused", "custen_cahn_set_graph", "custen_debug_bands", "custen_cahn_slab_create",
-       "custen_cahn_slab_buffer", "custen_cahn_slab_handle", "custen_cahn_slab_current", "custen_cahn_slab_phase",
-       "custen_cahn_slab_set_field", "custen_cahn_slab_get_field",
+       "custen_cahn_slab_export", "custen_cahn_slab_connect", "custen_cahn_slab_connect_local", "custen_cahn_slab_set_field",
+       "custen_cahn_slab_set_fields", "custen_cahn_slab_get_field", "custen_cahn_slab_step", "custen_cahn_slab_time_steps",
+       "custen_cahn_slab_synchronize", "custen_cahn_slab_error", "custen_cahn_slab_set_timeout", "custen_cahn_slab_set_graph",
+       "custen_cahn_slab_partition_rows", "custen_cahn_slab_destroy", "custen_cahn_mg_create", "custen_cahn_mg_set_field",
+       "custen_cahn_mg_get_field", "custen_cahn_mg_step", "custen_cahn_mg_time_steps", "custen_cahn_mg_error",
+       "custen_cahn_mg_set_graph", "custen_cahn_mg_destroy", "custen_cahn_set_fields", "custen_cahn_write_snapshot", "custen_cahn_dt",
        "custen_set_handle_managed_policy", "custen_mem_advise", "custen_mem_prefetch", "custen_fill_hash",
        "custen_slab_create", "custen_slab_export", "custen_slab_connect", "custen_slab_field", "custen_slab_rows",
        "custen_slab_compute", "custen_slab_swap", "custen_slab_run", "custen_slab_run_plain", "custen_slab_time_run",
@@ -49,7 +53,7 @@ EXPORTED = (
        "custen_slab_destroy", "custen_mg_create", "custen_mg_scatter", "custen_mg_gather", "custen_mg_fill_output",
        "custen_mg_compute", "custen_mg_swap", "custen_mg_run", "custen_mg_synchronize", "custen_mg_error", "custen_mg_slab",
        "custen_mg_destroy", "custen_device_numa_node", "custen_host_alloc_near", "custen_host_free_near", "custen_link_probe",
-       "custen_cahn_set_partition_rows", "custen_cahn_config", "custen_pent_part_host", "custen_pent_part_choose_np"]
+       "custen_cahn_set_partition_rows", "custen_cahn_config", "custen_pent_part_host", "custen_pent_part_choose_np", "custen_pent_part_device"]
 )
 
 _lib = None
@@ -116,10 +120,31 @@ def load():
     lib.custen_cahn_set_graph.argtypes, lib.custen_cahn_set_graph.restype = [_c_int], None
     lib.custen_cahn_slab_create.argtypes = [_c_int, _c_int, _c_int] + [ctypes.c_double] * 4 + [_c_int]
     lib.custen_cahn_slab_create.restype = ctypes.c_void_p
-    lib.custen_cahn_slab_buffer.argtypes, lib.custen_cahn_slab_buffer.restype = [_c_void_p, _c_int], ctypes.c_void_p
-    lib.custen_cahn_slab_handle.argtypes, lib.custen_cahn_slab_handle.restype = [_c_void_p, _c_int], ctypes.c_void_p
-    lib.custen_cahn_slab_current.argtypes, lib.custen_cahn_slab_current.restype = [_c_void_p], _c_int
-    lib.custen_cahn_slab_phase.argtypes, lib.custen_cahn_slab_phase.restype = [_c_void_p, _c_int], None
+    lib.custen_cahn_slab_export.argtypes, lib.custen_cahn_slab_export.restype = [_c_void_p, _c_void_p], None
+    lib.custen_cahn_slab_connect.argtypes, lib.custen_cahn_slab_connect.restype = [_c_void_p, _c_void_p, _c_void_p], None
+    lib.custen_cahn_slab_connect_local.argtypes, lib.custen_cahn_slab_connect_local.restype = [_c_void_p] * 3, None
+    lib.custen_cahn_slab_set_fields.argtypes, lib.custen_cahn_slab_set_fields.restype = [_c_void_p] * 3, None
+    lib.custen_cahn_slab_step.argtypes, lib.custen_cahn_slab_step.restype = [_c_void_p, _c_int], None
+    lib.custen_cahn_slab_time_steps.argtypes, lib.custen_cahn_slab_time_steps.restype = [_c_void_p, _c_int], ctypes.c_float
+    lib.custen_cahn_slab_synchronize.argtypes, lib.custen_cahn_slab_synchronize.restype = [_c_void_p], None
+    lib.custen_cahn_slab_error.argtypes, lib.custen_cahn_slab_error.restype = [_c_void_p], _c_int
+    lib.custen_cahn_slab_set_timeout.argtypes, lib.custen_cahn_slab_set_timeout.restype = [_c_void_p, ctypes.c_double], None
+    lib.custen_cahn_slab_set_graph.argtypes, lib.custen_cahn_slab_set_graph.restype = [_c_void_p, _c_int], None
+    lib.custen_cahn_slab_partition_rows.argtypes, lib.custen_cahn_slab_partition_rows.restype = [_c_void_p], _c_int
+    lib.custen_cahn_slab_destroy.argtypes, lib.custen_cahn_slab_destroy.restype = [_c_void_p], None
+    lib.custen_cahn_mg_create.argtypes = [_c_int, _c_int, _c_void_p] + [ctypes.c_double] * 4
+    lib.custen_cahn_mg_create.restype = ctypes.c_void_p
+    lib.custen_cahn_mg_set_field.argtypes, lib.custen_cahn_mg_set_field.restype = [_c_void_p, _c_void_p], None
+    lib.custen_cahn_mg_get_field.argtypes, lib.custen_cahn_mg_get_field.restype = [_c_void_p, _c_void_p], None
+    lib.custen_cahn_mg_step.argtypes, lib.custen_cahn_mg_step.restype = [_c_void_p, _c_int], None
+    lib.custen_cahn_mg_time_steps.argtypes, lib.custen_cahn_mg_time_steps.restype = [_c_void_p, _c_int], ctypes.c_float
+    lib.custen_cahn_mg_error.argtypes, lib.custen_cahn_mg_error.restype = [_c_void_p], _c_int
+    lib.custen_cahn_mg_set_graph.argtypes, lib.custen_cahn_mg_set_graph.restype = [_c_void_p, _c_int], None
+    lib.custen_cahn_mg_destroy.argtypes, lib.custen_cahn_mg_destroy.restype = [_c_void_p], None
+    lib.custen_cahn_set_fields.argtypes, lib.custen_cahn_set_fields.restype = [_c_void_p] * 3, None
+    lib.custen_cahn_write_snapshot.argtypes = [_c_void_p, ctypes.c_char_p, ctypes.c_double]
+    lib.custen_cahn_write_snapshot.restype = _c_int
+    lib.custen_cahn_dt.argtypes, lib.custen_cahn_dt.restype = [_c_void_p], ctypes.c_double
     lib.custen_cahn_slab_set_field.argtypes, lib.custen_cahn_slab_set_field.restype = [_c_void_p, _c_void_p], None
     lib.custen_cahn_slab_get_field.argtypes, lib.custen_cahn_slab_get_field.restype = [_c_void_p, _c_void_p], None
     lib.custen_debug_bands.argtypes = [_c_int] * 14 + [_c_void_p, _c_int]
@@ -166,6 +191,8 @@ def load():
     lib.custen_cahn_set_partition_rows.argtypes, lib.custen_cahn_set_partition_rows.restype = [_c_int], None
     lib.custen_cahn_config.argtypes, lib.custen_cahn_config.restype = [_c_void_p, _c_int, _c_int], _c_int
     lib.custen_pent_part_host.argtypes, lib.custen_pent_part_host.restype = [_c_int, _c_int, _c_void_p, _c_void_p, _c_void_p], _c_int
+    lib.custen_pent_part_device.argtypes = [_c_int, _c_int, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_int]
+    lib.custen_pent_part_device.restype = _c_int
     lib.custen_pent_part_choose_np.argtypes, lib.custen_pent_part_choose_np.restype = [_c_int, _c_int], _c_int
     _lib = lib
     return lib

@@ -28,10 +28,15 @@ class CahnHilliard:
         """The pentadiagonal solve in force (2 falls back to 0 where the partitioned layout cannot take the grid)."""
         return self.lib.custen_cahn_config(self.h, 0, -1)
 
-    def set_field(self, c0):
+    def set_field(self, c0, c_old=None):
+        """c(t = 0); c_old = c(t = -dt) (default: the same field, like the reference's initial condition)."""
         c0 = np.ascontiguousarray(c0, dtype=np.float64)
         assert c0.shape == (self.n, self.n)
-        self.lib.custen_cahn_set_field(self.h, c0.ctypes.data)
+        if c_old is None:
+            self.lib.custen_cahn_set_field(self.h, c0.ctypes.data)
+        else:
+            c_old = np.ascontiguousarray(c_old, dtype=np.float64)
+            self.lib.custen_cahn_set_fields(self.h, c0.ctypes.data, c_old.ctypes.data)
 
     def step(self, nsteps=1):
         self.lib.custen_cahn_step(self.h, nsteps)
@@ -45,94 +50,78 @@ class CahnHilliard:
         """Milliseconds per step over `nsteps` steps (CUDA events)."""
         return self.lib.custen_cahn_time_steps(self.h, nsteps) / nsteps
 
+    @property
+    def dt(self):
+        return self.lib.custen_cahn_dt(self.h)
+
+    def write_snapshot(self, directory, time):
+        """c(t) into <directory>/cahn_hilliard_<time>.bin (reference: Print_Out, cuPentCahnADI.cu:103-140)."""
+        if self.lib.custen_cahn_write_snapshot(self.h, str(directory).encode(), float(time)) != 0:
+            raise OSError(f"cannot write a snapshot into {directory}")
+
     def destroy(self):
         if self.h:
             self.lib.custen_cahn_destroy(self.h)
             self.h = None
 
 
-class _DeviceBuffer:
-    """Zero-copy torch view of a raw device pointer (CUDA array interface)."""
-
-    def __init__(self, ptr, count):
-        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
-
-
 class CahnHilliardSlab:
-    """The same solver on y-slabs over several GPUs (one process per GPU, torch.distributed initialised, NCCL).
+    """The tolerance-mode solver on y-slabs over several GPUs, one process per GPU (torch.distributed initialised; it is
+    used for the rendezvous only: 64-byte CUDA IPC handles and two barriers - no collective on the data path).
 
-    Rank g owns rows [g n/world, (g+1) n/world).  Stencil halo rows are read in place from the neighbours' memory
-    (CUDA IPC, custen_set_slab); the y-direction solve needs whole columns, so each step makes two all-to-all
-    transposes (torch.distributed.all_to_all_single) between the phases of custen_cahn_slab_phase.  Results are
-    bit-identical to the single-GPU solver: every system is solved by one thread in the same order.
+    Rank g owns rows [g n/world, (g+1) n/world).  Halo rows and the y-direction partitions' interface values are read in
+    place from the two neighbours' memory; the slabs order themselves on the device (include/custen_c.h,
+    custen_cahn_slab_*).  Results are bit-identical to CahnHilliard(solver=2) on one GPU.
     """
 
-    def __init__(self, n, D=1.0, gamma=0.01, lx=16.0 * math.pi, dt_over_dx=0.1, group=None):
+    def __init__(self, n, D=1.0, gamma=0.01, lx=16.0 * math.pi, dt_over_dx=0.1, group=None, device=None):
         import ctypes
         import torch
         import torch.distributed as dist
-        self.torch, self.dist, self.ctypes = torch, dist, ctypes
+        self.torch, self.dist = torch, dist
         self.lib = lib = _lib.load()
         self.group = group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        if n % self.world or (n // self.world) < 4:
+        if n % self.world:
             raise ValueError("n must be divisible by the number of ranks")
         self.n, self.rows = n, n // self.world
-        dev = torch.cuda.current_device()
+        dev = torch.cuda.current_device() if device is None else device
         self.h = lib.custen_cahn_slab_create(n, self.rank, self.world, D, gamma, lx, dt_over_dx, dev)
-        count = n * self.rows
-        buf = lambda k: lib.custen_cahn_slab_buffer(self.h, k)  # noqa: E731
-        self.t_send1 = torch.as_tensor(_DeviceBuffer(buf(3), count), device=f"cuda:{dev}")
-        self.t_recv = torch.as_tensor(_DeviceBuffer(buf(4), count), device=f"cuda:{dev}")
-        self.t_send2 = torch.as_tensor(_DeviceBuffer(buf(5), count), device=f"cuda:{dev}")
-        # neighbours' field / cBar buffers and barrier flags through CUDA IPC
-        up, down = (self.rank - 1) % self.world, (self.rank + 1) % self.world
-        self._mapped, opened = [], {}
+        if not self.h:
+            raise ValueError(f"the partitioned layout cannot take n = {n} on {self.world} slabs")
+        if self.world > 1:
+            mine = (ctypes.c_char * 64)()
+            lib.custen_cahn_slab_export(self.h, ctypes.addressof(mine))
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(mine), group=group)
+            up = (ctypes.c_char * 64).from_buffer_copy(handles[(self.rank - 1) % self.world])
+            down = (ctypes.c_char * 64).from_buffer_copy(handles[(self.rank + 1) % self.world])
+            lib.custen_cahn_slab_connect(self.h, ctypes.addressof(up), ctypes.addressof(down))
+            dist.barrier(group=group)
 
-        def exchange(ptr):
-            hd, off = (ctypes.c_char * 64)(), ctypes.c_size_t(0)
-            lib.custen_ipc_export(ptr, ctypes.addressof(hd), ctypes.byref(off))
-            hs, offs = [None] * self.world, [None] * self.world
-            dist.all_gather_object(hs, bytes(hd), group=group)
-            dist.all_gather_object(offs, int(off.value), group=group)
-
-            def peer(r):
-                key = hs[r]
-                if key not in opened:
-                    b = (ctypes.c_char * 64).from_buffer_copy(hs[r])
-                    opened[key] = lib.custen_ipc_open(ctypes.addressof(b))
-                    self._mapped.append(opened[key])
-                return opened[key] + offs[r]
-            return peer(up), peer(down)
-
-        row = n * 8
-        for which, T in ((0, 1), (1, 1), (2, 2)):   # nonlinear term: 3 x 3 (T = B = 1); linear term: 5 x 5 (T = B = 2)
-            p_up, p_down = exchange(buf(which))
-            handle = lib.custen_cahn_slab_handle(self.h, which)
-            lib.custen_set_slab(handle, p_up + (self.rows - T) * row, p_down, 0, 0)
-        self._flags = lib.custen_device_alloc(16)
-        self._up_flags, self._down_flags = exchange(self._flags)
-        self._epoch = 0
-        dist.barrier(group=group)
-
-    def set_field(self, c0_rows):
+    def set_field(self, c0_rows, c_old_rows=None):
         c0_rows = np.ascontiguousarray(c0_rows, dtype=np.float64)
         assert c0_rows.shape == (self.rows, self.n)
-        self.lib.custen_cahn_slab_set_field(self.h, c0_rows.ctypes.data)
-        self.torch.cuda.synchronize()
-        self.dist.barrier(group=self.group)
+        if c_old_rows is None:
+            self.lib.custen_cahn_slab_set_field(self.h, c0_rows.ctypes.data)
+        else:
+            c_old_rows = np.ascontiguousarray(c_old_rows, dtype=np.float64)
+            self.lib.custen_cahn_slab_set_fields(self.h, c0_rows.ctypes.data, c_old_rows.ctypes.data)
+        if self.world > 1:
+            self.dist.barrier(group=self.group)   # the neighbours' halo rows are in place before anyone steps
 
     def step(self, nsteps=1):
-        lib, dist = self.lib, self.dist
-        for _ in range(nsteps):
-            lib.custen_cahn_slab_phase(self.h, 0)
-            self._epoch += 1
-            lib.custen_peer_barrier(None, self._up_flags, self._down_flags, self._flags, self._epoch)
-            lib.custen_cahn_slab_phase(self.h, 1)
-            dist.all_to_all_single(self.t_recv, self.t_send1, group=self.group)
-            lib.custen_cahn_slab_phase(self.h, 2)
-            dist.all_to_all_single(self.t_recv, self.t_send2, group=self.group)
-            lib.custen_cahn_slab_phase(self.h, 3)
+        self.lib.custen_cahn_slab_step(self.h, nsteps)
+
+    def time_steps(self, nsteps):
+        """Milliseconds per step over `nsteps` steps on this rank (CUDA events on the slab's stream)."""
+        return self.lib.custen_cahn_slab_time_steps(self.h, nsteps) / nsteps
+
+    def synchronize(self):
+        self.lib.custen_cahn_slab_synchronize(self.h)
+
+    def error(self):
+        return self.lib.custen_cahn_slab_error(self.h)
 
     def field(self):
         out = np.empty((self.rows, self.n))
@@ -141,10 +130,45 @@ class CahnHilliardSlab:
 
     def destroy(self):
         if self.h:
-            self.torch.cuda.synchronize()
-            self.dist.barrier(group=self.group)
-            self.lib.custen_cahn_destroy(self.h)
-            for p in self._mapped:
-                self.lib.custen_ipc_close(p)
-            self.lib.custen_device_free(self._flags)
+            self.lib.custen_cahn_slab_synchronize(self.h)
+            if self.world > 1:
+                self.dist.barrier(group=self.group)   # nobody unmaps memory a neighbour may still be reading
+            self.lib.custen_cahn_slab_destroy(self.h)
+            self.h = None
+
+
+class CahnHilliardMultiGpu:
+    """The same slabs driven by ONE process over `ngpus` GPUs (custen_cahn_mg_*)."""
+
+    def __init__(self, n, ngpus, D=1.0, gamma=0.01, lx=16.0 * math.pi, dt_over_dx=0.1, devices=None):
+        import ctypes
+        self.lib = _lib.load()
+        self.n, self.ngpus = n, ngpus
+        devs = (ctypes.c_int * ngpus)(*(devices if devices is not None else range(ngpus)))
+        self.h = self.lib.custen_cahn_mg_create(n, ngpus, ctypes.addressof(devs), D, gamma, lx, dt_over_dx)
+        if not self.h:
+            raise ValueError(f"the partitioned layout cannot take n = {n} on {ngpus} slabs")
+
+    def set_field(self, c0):
+        c0 = np.ascontiguousarray(c0, dtype=np.float64)
+        assert c0.shape == (self.n, self.n)
+        self.lib.custen_cahn_mg_set_field(self.h, c0.ctypes.data)
+
+    def step(self, nsteps=1):
+        self.lib.custen_cahn_mg_step(self.h, nsteps)
+
+    def time_steps(self, nsteps):
+        return self.lib.custen_cahn_mg_time_steps(self.h, nsteps) / nsteps
+
+    def error(self):
+        return self.lib.custen_cahn_mg_error(self.h)
+
+    def field(self):
+        out = np.empty((self.n, self.n))
+        self.lib.custen_cahn_mg_get_field(self.h, out.ctypes.data)
+        return out
+
+    def destroy(self):
+        if self.h:
+            self.lib.custen_cahn_mg_destroy(self.h)
             self.h = None

@@ -151,7 +151,7 @@ int part_choose_np(int n, int wanted)
     // a partition is one TMA box: at most 256 rows; at least two partitions so that the ring has a neighbour
     const int cand[] = {wanted, 128, 64, 32, 256};
     for (int c : cand)
-        if (c >= 32 && c <= 256 && c % 32 == 0 && n % c == 0 && n / c >= 2) return c;
+        if ((c == 32 || c == 64 || c == 128 || c == 256) && n % c == 0 && n / c >= 2) return c;
     return 0;
 }
 
@@ -331,38 +331,17 @@ void part_solve_host(const PartPlan* pl, const double* rhs, double* x)
 
 __device__ __forceinline__ unsigned smem_a(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-// One warp = one tile of 32 systems x np rows.  Lane 0 moves the tile and the two coefficient tables in with the
-// async proxy (one tensor copy + two bulk copies on one mbarrier) and the solved tile out; the warp runs the two sweeps
-// in shared memory: per row one 64-bit load and store per lane (conflict free) and one broadcast coefficient load.
-__global__ void __launch_bounds__(32) k_pent_part(const __grid_constant__ CUtensorMap tm, const double* __restrict__ tabF,
-                                                  const double* __restrict__ tabB, double* __restrict__ G, int nsys, int np)
+__device__ __forceinline__ void bar_init(unsigned a_bar)
 {
-    extern __shared__ __align__(128) unsigned char part_smem[];
-    double* tile = reinterpret_cast<double*>(part_smem);                 // [np][32]
-    double* sF = tile + (size_t)np * 32;                                 // [np][4]  {-s', -l', 1/d, 0}
-    double* sB = sF + (size_t)np * 4;                                    // [np][2]  {-u, -w}
-    unsigned long long* bar = reinterpret_cast<unsigned long long*>(sB + (size_t)np * 2);
-    const int lane = threadIdx.x;
-    const int sys0 = blockIdx.x * 32, p = blockIdx.y, row0 = p * np;
-    const unsigned a_bar = smem_a(bar);
-    if (lane == 0)
-    {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a_bar) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        const unsigned bytes = (unsigned)np * (32 * 8 + 4 * 8 + 2 * 8);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a_bar), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-                         smem_a(tile)),
-                     "l"(&tm), "r"(sys0), "r"(row0), "r"(a_bar)
-                     : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_a(sF)),
-                     "l"(tabF), "r"((unsigned)np * 32u), "r"(a_bar)
-                     : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_a(sB)),
-                     "l"(tabB), "r"((unsigned)np * 16u), "r"(a_bar)
-                     : "memory");
-    }
-    __syncwarp();
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a_bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bar_expect(unsigned a_bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a_bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_wait(unsigned a_bar)
+{
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -371,42 +350,196 @@ __global__ void __launch_bounds__(32) k_pent_part(const __grid_constant__ CUtens
         "@!p bra PART_WAIT_%=;\n"
         "}\n" ::"r"(a_bar)
         : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned a_bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(a_bar)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, unsigned src, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
 
-    double* col = tile + lane;
-    // forward: y_i = rd_i b_i - s'_i y_{i-2} - l'_i y_{i-1}; only the last fma waits for the previous row
-    double y2 = 0.0, y1 = 0.0;
-#pragma unroll 8
-    for (int i = 0; i < np; ++i)
+// The two sweeps of one partition for one system per lane.  at(i) is the lane's i-th unknown in shared memory; the
+// tables are read with broadcast loads.  Rows go through in blocks of R: the loads of block k+1 are issued before the
+// dependent chain of block k (one FMA per row: the term in y_{i-2} and the scaling by 1/d are off the chain), so the
+// chain never waits for shared memory.  CORR: the right-hand side still lacks the x-direction solve's rank-4
+// correction, b_i - (w0 q0_i + w1 q1_i + w2 q2_i + w3 q3_i), applied while the block is staged.
+template <int NP, int R, bool CORR, class At>
+__device__ __forceinline__ void sweeps(At at, const double* sF, const double* sB, const double* sQ, const double (&w)[4],
+                                       double (&g)[4])
+{
+    static_assert(NP % R == 0 && R % 2 == 0, "block height");
+    double b[R], cs[R], cl[R];
+    auto stage = [&](int i0, double (&raw)[R], double (&rs)[R], double (&rl)[R], double (&rd)[R], double (&q)[CORR ? 4 : 1][R]) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) raw[r] = *at(i0 + r);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+        {
+            const double2 c01 = *reinterpret_cast<const double2*>(sF + 4 * (i0 + r));
+            rs[r] = c01.x;
+            rl[r] = c01.y;
+            rd[r] = sF[4 * (i0 + r) + 2];
+        }
+        if (CORR)
+        {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int r = 0; r < R; r += 2)
+                {
+                    const double2 v = *reinterpret_cast<const double2*>(sQ + k * NP + i0 + r);
+                    q[k][r] = v.x;
+                    q[k][r + 1] = v.y;
+                }
+        }
+    };
+    auto finish = [&](double (&raw)[R], double (&rs)[R], double (&rl)[R], double (&rd)[R], double (&q)[CORR ? 4 : 1][R]) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+        {
+            double v = raw[r];
+            if (CORR)
+            {
+                double corr = w[0] * q[0][r];
+                corr = fma(w[1], q[1][r], corr);
+                corr = fma(w[2], q[2][r], corr);
+                corr = fma(w[3], q[3][r], corr);
+                v -= corr;
+            }
+            b[r] = rd[r] * v;
+            cs[r] = rs[r];
+            cl[r] = rl[r];
+        }
+    };
     {
-        const double2 c01 = *reinterpret_cast<const double2*>(sF + 4 * i);
-        const double rd = sF[4 * i + 2];
-        const double t = fma(c01.x, y2, rd * col[i * 32]);
-        const double v = fma(c01.y, y1, t);
-        col[i * 32] = v;
-        y2 = y1;
-        y1 = v;
+        double raw[R], rs[R], rl[R], rd[R], q[CORR ? 4 : 1][R];
+        stage(0, raw, rs, rl, rd, q);
+        finish(raw, rs, rl, rd, q);
+    }
+    // forward: y_i = b_i / d_i - s'_i y_{i-2} - l'_i y_{i-1}
+    double y2 = 0.0, y1 = 0.0;
+#pragma unroll 1
+    for (int i0 = 0; i0 < NP; i0 += R)
+    {
+        double raw[R], rs[R], rl[R], rd[R], q[CORR ? 4 : 1][R];
+        const bool more = i0 + R < NP;
+        if (more) stage(i0 + R, raw, rs, rl, rd, q);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+        {
+            const double t = fma(cs[r], y2, b[r]);
+            const double v = fma(cl[r], y1, t);
+            *at(i0 + r) = v;
+            y2 = y1;
+            y1 = v;
+        }
+        if (more) finish(raw, rs, rl, rd, q);
     }
     // backward: x_i = y_i - w_i x_{i+2} - u_i x_{i+1}
-    double x1 = 0.0, x2 = 0.0, gb0 = 0.0, gb1 = 0.0;
-#pragma unroll 8
-    for (int i = np - 1; i >= 0; --i)
+    double x1 = 0.0, x2 = 0.0;
+    double yb[R], cu[R], cw[R];
+    auto stage_b = [&](int i0, double (&ry)[R], double (&ru)[R], double (&rw)[R]) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) ry[r] = *at(i0 + r);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+        {
+            const double2 c = *reinterpret_cast<const double2*>(sB + 2 * (i0 + r));
+            ru[r] = c.x;
+            rw[r] = c.y;
+        }
+    };
+    stage_b(NP - R, yb, cu, cw);
+#pragma unroll 1
+    for (int i0 = NP - R; i0 >= 0; i0 -= R)
     {
-        const double2 c = *reinterpret_cast<const double2*>(sB + 2 * i);
-        const double t = fma(c.y, x2, col[i * 32]);
-        const double v = fma(c.x, x1, t);
-        col[i * 32] = v;
-        x2 = x1;
-        x1 = v;
-        if (i == np - 1) gb1 = v;
-        if (i == np - 2) gb0 = v;
+        double ry[R], ru[R], rw[R];
+        const bool more = i0 > 0;
+        if (more) stage_b(i0 - R, ry, ru, rw);
+#pragma unroll
+        for (int r = R - 1; r >= 0; --r)
+        {
+            const double t = fma(cw[r], x2, yb[r]);
+            const double v = fma(cu[r], x1, t);
+            *at(i0 + r) = v;
+            x2 = x1;
+            x1 = v;
+            if (i0 + r == NP - 1) g[3] = v;
+            if (i0 + r == NP - 2) g[2] = v;
+        }
+        if (more)
+        {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+            {
+                yb[r] = ry[r];
+                cu[r] = ru[r];
+                cw[r] = rw[r];
+            }
+        }
     }
-    // the tile's interface values: first two and last two unknowns of the local solution
+    g[0] = x1;
+    g[1] = x2;
+}
+
+// Unknowns along the rows of the array, systems contiguous (the y-direction solve on data[row][sys]).  One warp = one
+// tile of NP rows x 32 systems: lane 0 moves the tile and the tables in with the async proxy (one tensor copy + bulk
+// copies on one mbarrier) and the solved tile out.  CORR: the data is the x-direction solve's partition-local result;
+// its correction needs the four interface unknowns qx[(px * 4 + k) * q_nsys + row] of the x-partition px the tile's 32
+// columns lie in, and the spike rows wv[4 * column-in-partition + k].
+template <int NP, int R, bool CORR>
+__global__ void __launch_bounds__(32) k_part_rows(const __grid_constant__ CUtensorMap tm, const double* __restrict__ tabF,
+                                                  const double* __restrict__ tabB, double* __restrict__ G, int nsys,
+                                                  const double* __restrict__ qx, const double* __restrict__ wv, int q_nsys)
+{
+    extern __shared__ __align__(128) unsigned char part_smem[];
+    double* tile = reinterpret_cast<double*>(part_smem);   // [NP][32]
+    double* sF = tile + NP * 32;                           // [NP][4]  {-s', -l', 1/d, 0}
+    double* sB = sF + NP * 4;                              // [NP][2]  {-u, -w}
+    double* sQ = sB + NP * 2;                              // [4][NP]
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(sQ + (CORR ? 4 * NP : 0));
+    const int lane = threadIdx.x;
+    const int sys0 = blockIdx.x * 32, p = blockIdx.y, row0 = p * NP;
+    const unsigned a_bar = smem_a(bar);
+    if (lane == 0)
+    {
+        bar_init(a_bar);
+        bar_expect(a_bar, (unsigned)NP * (32 * 8 + 4 * 8 + 2 * 8 + (CORR ? 4 * 8 : 0)));
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                         smem_a(tile)),
+                     "l"(&tm), "r"(sys0), "r"(row0), "r"(a_bar)
+                     : "memory");
+        bulk_g2s(smem_a(sF), tabF, NP * 32u, a_bar);
+        bulk_g2s(smem_a(sB), tabB, NP * 16u, a_bar);
+        if (CORR)
+        {
+            const int px = sys0 / NP;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) bulk_g2s(smem_a(sQ + k * NP), qx + ((size_t)px * 4 + k) * q_nsys + row0, NP * 8u, a_bar);
+        }
+    }
+    double w[4] = {0.0, 0.0, 0.0, 0.0};
+    if (CORR)
+    {
+        const double2* wp = reinterpret_cast<const double2*>(wv + 4 * (sys0 % NP + lane));
+        const double2 w01 = wp[0], w23 = wp[1];
+        w[0] = w01.x; w[1] = w01.y; w[2] = w23.x; w[3] = w23.y;
+    }
+    __syncwarp();
+    bar_wait(a_bar);
+
+    double* col = tile + lane;
+    double g[4];
+    sweeps<NP, R, CORR>([col](int i) { return col + i * 32; }, sF, sB, sQ, w, g);
     double* gp = G + ((size_t)p * 4) * nsys + sys0 + lane;
-    gp[0] = x1;
-    gp[(size_t)nsys] = x2;
-    gp[(size_t)2 * nsys] = gb0;
-    gp[(size_t)3 * nsys] = gb1;
-    // results back through the async proxy
+    gp[0] = g[0];
+    gp[(size_t)nsys] = g[1];
+    gp[(size_t)2 * nsys] = g[2];
+    gp[(size_t)3 * nsys] = g[3];
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (lane == 0)
@@ -417,6 +550,49 @@ __global__ void __launch_bounds__(32) k_pent_part(const __grid_constant__ CUtens
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
+}
+
+// Unknowns contiguous, one system per array row (the x-direction solve on the grid's own layout, data[sys * ld + x]: no
+// transposes).  One warp = one tile of 32 systems x NP unknowns; every lane moves its own row with a bulk copy into a
+// row of NP + 2 doubles (16-byte pairs of the 32 lanes then fall into different banks) and walks along it.
+template <int NP, int R>
+__global__ void __launch_bounds__(32) k_part_cols(double* __restrict__ data, int ld, const double* __restrict__ tabF,
+                                                  const double* __restrict__ tabB, double* __restrict__ G, int nsys)
+{
+    constexpr int PT = NP + 2;
+    extern __shared__ __align__(128) unsigned char part_smem[];
+    double* tile = reinterpret_cast<double*>(part_smem);   // [32][PT]
+    double* sF = tile + 32 * PT;
+    double* sB = sF + NP * 4;
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(sB + NP * 2);
+    const int lane = threadIdx.x;
+    const int sys0 = blockIdx.x * 32, p = blockIdx.y;
+    const unsigned a_bar = smem_a(bar);
+    double* grow = data + (size_t)(sys0 + lane) * ld + (size_t)p * NP;
+    double* row = tile + lane * PT;
+    if (lane == 0)
+    {
+        bar_init(a_bar);
+        bar_expect(a_bar, (unsigned)NP * (32 * 8 + 4 * 8 + 2 * 8));
+        bulk_g2s(smem_a(sF), tabF, NP * 32u, a_bar);
+        bulk_g2s(smem_a(sB), tabB, NP * 16u, a_bar);
+    }
+    __syncwarp();
+    bulk_g2s(smem_a(row), grow, NP * 8u, a_bar);
+    bar_wait(a_bar);
+
+    const double w[4] = {0.0, 0.0, 0.0, 0.0};
+    double g[4];
+    sweeps<NP, R, false>([row](int i) { return row + i; }, sF, sB, nullptr, w, g);
+    double* gp = G + ((size_t)p * 4) * nsys + sys0 + lane;
+    gp[0] = g[0];
+    gp[(size_t)nsys] = g[1];
+    gp[(size_t)2 * nsys] = g[2];
+    gp[(size_t)3 * nsys] = g[3];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    bulk_s2g(grow, smem_a(row), NP * 8u);
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // q_p = sum_j Q_j gamma_{p+j} for this rank's partitions.  gptr[r] = rank r's interface array (P_loc x 4 x nsys), in peer
@@ -478,25 +654,78 @@ static bool make_tile_map(CUtensorMap* tm, double* data, int nsys, int nrows, in
 
 bool part_solve_supported(int nsys, int nrows_local, int np)
 {
-    return np >= 32 && np <= 256 && nsys % 32 == 0 && nrows_local % np == 0;
+    return (np == 32 || np == 64 || np == 128 || np == 256) && nsys % 32 == 0 && nrows_local % np == 0;
 }
 
-bool part_solve(const PartPlan* pl, double* data, int nsys, int nrows_local, double* G, cudaStream_t stream)
+// the shared-memory opt-in of a kernel, once per device and kernel (monotonic: never lowered)
+template <class K>
+static void opt_in(K kernel, size_t smem, size_t (&configured)[64])
 {
-    const int np = pl->np;
-    CUtensorMap tm;
-    if (!part_solve_supported(nsys, nrows_local, np) || !make_tile_map(&tm, data, nsys, nrows_local, np)) return false;
-    const size_t smem = (size_t)np * (32 + 4 + 2) * sizeof(double) + 16;
-    static size_t configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || smem > configured[dev])
     {
-        cudaFuncSetAttribute(k_pent_part, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (dev >= 0 && dev < 64) configured[dev] = smem;
     }
-    dim3 grid(nsys / 32, nrows_local / np);
-    k_pent_part<<<grid, 32, smem, stream>>>(tm, pl->tabF, pl->tabB, G, nsys, np);
+}
+
+template <int NP, bool CORR>
+static void launch_rows(const PartPlan* pl, const CUtensorMap& tm, int nsys, int nrows_local, double* G, const double* qx,
+                        int q_nsys, cudaStream_t stream)
+{
+    constexpr int R = CORR ? 4 : 8;
+    const size_t smem = (size_t)NP * (32 + 4 + 2 + (CORR ? 4 : 0)) * sizeof(double) + 16;
+    static size_t configured[64] = {};
+    opt_in(k_part_rows<NP, R, CORR>, smem, configured);
+    dim3 grid(nsys / 32, nrows_local / NP);
+    k_part_rows<NP, R, CORR><<<grid, 32, smem, stream>>>(tm, pl->tabF, pl->tabB, G, nsys, qx, pl->wv, q_nsys);
+}
+
+bool part_solve_rows(const PartPlan* pl, double* data, int nsys, int nrows_local, double* G, const double* qx, int q_nsys,
+                     cudaStream_t stream)
+{
+    const int np = pl->np;
+    CUtensorMap tm;
+    if (!part_solve_supported(nsys, nrows_local, np) || !make_tile_map(&tm, data, nsys, nrows_local, np)) return false;
+#define ROWS_CASE(NP_)                                                                                      \
+    case NP_:                                                                                               \
+        if (qx) launch_rows<NP_, true>(pl, tm, nsys, nrows_local, G, qx, q_nsys, stream);                   \
+        else launch_rows<NP_, false>(pl, tm, nsys, nrows_local, G, nullptr, 0, stream);                     \
+        break;
+    switch (np)
+    {
+        ROWS_CASE(32)
+        ROWS_CASE(64)
+        ROWS_CASE(128)
+        ROWS_CASE(256)
+    }
+#undef ROWS_CASE
+    return true;
+}
+
+template <int NP>
+static void launch_cols(const PartPlan* pl, double* data, int nsys, int ld, double* G, cudaStream_t stream)
+{
+    constexpr int R = 8;
+    const size_t smem = ((size_t)32 * (NP + 2) + (size_t)NP * (4 + 2)) * sizeof(double) + 16;
+    static size_t configured[64] = {};
+    opt_in(k_part_cols<NP, R>, smem, configured);
+    dim3 grid(nsys / 32, pl->P);
+    k_part_cols<NP, R><<<grid, 32, smem, stream>>>(data, ld, pl->tabF, pl->tabB, G, nsys);
+}
+
+bool part_solve_cols(const PartPlan* pl, double* data, int nsys, int ld, double* G, cudaStream_t stream)
+{
+    const int np = pl->np;
+    if (!part_solve_supported(nsys, ld, np) || ld != pl->n || ((uintptr_t)data & 15)) return false;
+    switch (np)
+    {
+        case 32: launch_cols<32>(pl, data, nsys, ld, G, stream); break;
+        case 64: launch_cols<64>(pl, data, nsys, ld, G, stream); break;
+        case 128: launch_cols<128>(pl, data, nsys, ld, G, stream); break;
+        case 256: launch_cols<256>(pl, data, nsys, ld, G, stream); break;
+    }
     return true;
 }
 
@@ -509,6 +738,89 @@ void part_reduce(const PartPlan* pl, const double* const* gptr_dev, int world, i
 }
 
 }  // namespace custen_cahn
+
+// ---- the device path on caller-supplied systems (kernel-level parity tests) ----------------------------------------------
+namespace custen_cahn {
+
+// x = g - (W0 q0 + W1 q1 + V0 q2 + V1 q3), the expression the consumers of a solve use; rows != 0: data[i * nsys + sys],
+// else data[sys * n + i]
+__global__ void k_apply_correction(double* data, const double* __restrict__ q, const double* __restrict__ wv, int n, int nsys,
+                                   int np, int rows)
+{
+    const size_t total = (size_t)n * nsys;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x)
+    {
+        const int i = rows ? (int)(e / nsys) : (int)(e % n);
+        const int sys = rows ? (int)(e % nsys) : (int)(e / n);
+        const int p = i / np;
+        const double* w = wv + 4 * (i - p * np);
+        const double* qp = q + ((size_t)p * 4) * nsys + sys;
+        double corr = w[0] * qp[0];
+        corr = fma(w[1], qp[(size_t)nsys], corr);
+        corr = fma(w[2], qp[(size_t)2 * nsys], corr);
+        corr = fma(w[3], qp[(size_t)3 * nsys], corr);
+        data[e] -= corr;
+    }
+}
+
+}  // namespace custen_cahn
+
+extern "C" {
+
+// Solve nsys periodic pentadiagonal systems of n unknowns with the DEVICE kernels (current device, legacy stream).
+//   layout 0: rhs[sys * n + i] (unknowns contiguous: k_part_cols),  layout 1: rhs[i * nsys + sys] (k_part_rows);
+//   layout 2: nsys == n, the ADI pair on an n x n array a[y][x]: the systems along x, then - with the first solve's
+//             correction applied while the tiles are staged - the systems along y.
+// Bit-identical to custen_pent_part_host applied to every system (tests/test_pent_part_gpu.py).  Returns the number of
+// coupling blocks kept, 0 if the layout cannot take the kernels.
+int custen_pent_part_device(int n, int np, const double* coef5, int nsys, const double* rhs_host, double* x_host, int layout)
+{
+    using namespace custen_cahn;
+    if (layout == 2 && nsys != n) return 0;
+    PartPlan* pl = part_plan_create(n, np, coef5, true);
+    if (!pl) return 0;
+    const int P = pl->P;
+    const size_t N = (size_t)n * nsys, gcount = (size_t)4 * P * nsys;
+    double *data = nullptr, *G = nullptr, *q = nullptr, *G2 = nullptr, *q2 = nullptr;
+    const double** gptr = nullptr;
+    cudaMalloc(&data, N * sizeof(double));
+    cudaMalloc(&G, gcount * sizeof(double));
+    cudaMalloc(&q, gcount * sizeof(double));
+    cudaMalloc(&G2, gcount * sizeof(double));
+    cudaMalloc(&q2, gcount * sizeof(double));
+    cudaMalloc(&gptr, 2 * sizeof(double*));
+    const double* ptrs[2] = {G, G2};
+    cudaMemcpy(gptr, ptrs, sizeof ptrs, cudaMemcpyHostToDevice);
+    cudaMemcpy(data, rhs_host, N * sizeof(double), cudaMemcpyHostToDevice);
+    bool ok = true;
+    if (layout == 0 || layout == 2)
+    {
+        ok = part_solve_cols(pl, data, nsys, n, G, 0);
+        part_reduce(pl, gptr, 1, 0, P, nsys, q, 0);
+        if (layout == 0) k_apply_correction<<<1184, 256>>>(data, q, pl->wv, n, nsys, np, 0);
+    }
+    if (ok && layout == 1)
+    {
+        ok = part_solve_rows(pl, data, nsys, n, G, nullptr, 0, 0);
+        part_reduce(pl, gptr, 1, 0, P, nsys, q, 0);
+        k_apply_correction<<<1184, 256>>>(data, q, pl->wv, n, nsys, np, 1);
+    }
+    if (ok && layout == 2)
+    {
+        ok = part_solve_rows(pl, data, n, n, G2, q, n, 0);
+        part_reduce(pl, gptr + 1, 1, 0, P, n, q2, 0);
+        k_apply_correction<<<1184, 256>>>(data, q2, pl->wv, n, n, np, 1);
+    }
+    cudaDeviceSynchronize();
+    ok = ok && cudaGetLastError() == cudaSuccess;
+    cudaMemcpy(x_host, data, N * sizeof(double), cudaMemcpyDeviceToHost);
+    for (void* p : {(void*)data, (void*)G, (void*)q, (void*)G2, (void*)q2, (void*)gptr}) cudaFree(p);
+    const int nb = pl->nb;
+    part_plan_destroy(pl);
+    return ok ? nb : 0;
+}
+
+}  // extern "C"
 
 // ---- host emulation for the CPU tests (no CUDA call is made when device_tables is false) -------------------------------
 extern "C" {

@@ -23,10 +23,18 @@ const double* part_plan_wv(const PartPlan* plan); // device table [np][4] = {W0,
 
 bool part_solve_supported(int nsys, int nrows_local, int np);
 
-// Local solves in place: data[row * nsys + sys], nrows_local rows (this GPU's share of the n-row systems, whole
-// partitions), plus the interface values G[(p_local * 4 + k) * nsys + sys], k = first, second, last-but-one, last unknown
-// of the partition's local solution.  Returns false (nothing enqueued) when the layout cannot take the TMA tiles.
-bool part_solve(const PartPlan* plan, double* data, int nsys, int nrows_local, double* G, cudaStream_t stream);
+// Local solves in place, unknowns along the array's rows: data[row * nsys + sys], nrows_local rows (this GPU's share of
+// the n-row systems, whole partitions), plus the interface values G[(p_local * 4 + k) * nsys + sys], k = first, second,
+// last-but-one, last unknown of the partition's local solution.  qx != nullptr: the data is the partition-local result
+// of part_solve_cols on the same array and still lacks that solve's correction; it is applied while the tiles are
+// staged (qx = that solve's interface unknowns from part_reduce, q_nsys = its number of systems = nrows_local).
+// Returns false (nothing enqueued) when the layout cannot take the tiles.
+bool part_solve_rows(const PartPlan* plan, double* data, int nsys, int nrows_local, double* G, const double* qx, int q_nsys,
+                     cudaStream_t stream);
+
+// Local solves in place, unknowns contiguous: data[sys * ld + x], x < ld = n (whole systems on this GPU), nsys systems.
+// G as above with P = n / np partitions.
+bool part_solve_cols(const PartPlan* plan, double* data, int nsys, int ld, double* G, cudaStream_t stream);
 
 // q[(p_local * 4 + k) * nsys + sys] = the four interface unknowns partition p_local needs for its correction
 // x = g - (W0 q0 + W1 q1 + V0 q2 + V1 q3).  gptr_dev: device array of `world` pointers to the ranks' G arrays.

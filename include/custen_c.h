@@ -216,35 +216,68 @@ void custen_cahn_set_fused(int on);                             /* 1: fused righ
 void custen_cahn_set_graph(int on);                             /* 1: replay the fused step from a CUDA graph (default), 0: kernel by kernel */
 /* The custen_cahn_set_* switches are the defaults for solvers created AFTERWARDS; every solver keeps its own copy
  * (custen_cahn_config changes one solver).
- * solver 2 (default): partitioned tolerance-mode solve (custen_b200/csrc/pent_part.cu) - within 1e-13 of the reference's
- * solver (cuPentBatch.cu:119-198 + BatchHyper.cu:195-259), not bit-identical; falls back to 0 where the layout cannot
- * take it (n % 32 != 0).  0: TMA-fed solve in the reference's operation order (bit-identical), 1: its cp.async twin. */
+ * solver 2 (default): partitioned tolerance-mode solve (custen_b200/csrc/pent_part.cu, step in cahn_part.cu) - within
+ * 1e-13 of the reference's solver per step (cuPentBatch.cu:119-198 + BatchHyper.cu:195-259), not bit-identical; falls
+ * back to 0 where the layout cannot take it (n not a multiple of 64).  0: TMA-fed solve in the reference's operation
+ * order (bit-identical), 1: its cp.async twin. */
 void custen_cahn_set_solver(int which);
-void custen_cahn_set_partition_rows(int np);                    /* rows per partition of solver 2: 32 .. 256, multiple of 32 (default 128) */
+void custen_cahn_set_partition_rows(int np);                    /* rows per partition of solver 2: 32, 64, 128 or 256 (default 128) */
 int custen_cahn_config(void* solver, int key, int value);       /* key 0 solver, 1 fused, 2 graph, 3 table rows; value < 0 queries */
 /* The partitioned algorithm's arithmetic on the host for ONE periodic pentadiagonal system (diagonals coef5 = a b c d e
  * at offsets -2 .. +2): pins tables and algorithm against a dense solve without a GPU.  Returns the number of
  * interface coupling blocks kept, 0 if (n, np) is not a valid partitioning. */
 int custen_pent_part_host(int n, int np, const double* coef5, const double* rhs, double* x);
 int custen_pent_part_choose_np(int n, int wanted);
+/* The same systems through the DEVICE kernels: layout 0 rhs[sys * n + i], 1 rhs[i * nsys + sys], 2 the ADI pair on an
+ * n x n array (along x, then along y); bit-identical to custen_pent_part_host per system. */
+int custen_pent_part_device(int n, int np, const double* coef5, int nsys, const double* rhs_host, double* x_host, int layout);
 void custen_cahn_set_table_rows(int rows);                      /* tuning / tests: coefficient rows staged per refill */
 
-/* The same solver on one y-slab of the grid (one process per GPU; BASELINE.json config 5 at 2-8 GPUs), driven phase by
- * phase so that the caller can place the neighbour barrier and the two all-to-all transposes between the phases
- * (custen_b200/cahn.py CahnHilliardSlab does this over torch.distributed / NCCL):
- *   phase 0: cBar = 2c - cOld          -> neighbour barrier (halo rows of c and cBar are read from peer memory)
- *   phase 1: both stencils, right-hand side, x-direction solve -> all-to-all of buffer 3 into buffer 4
- *   phase 2: gather whole columns, y-direction solve           -> all-to-all of buffer 5 into buffer 4
- *   phase 3: c(t + dt) = cBar + w, field buffers trade roles
- * buffers: 0 / 1 the two field buffers, 2 cBar, 3 x-solve result (n x rows), 4 receive buffer, 5 y-solve result (n x cols);
- * handles: 0 / 1 nonlinear term on field buffer 0 / 1, 2 linear term on cBar (for custen_set_slab). */
+/* Snapshot of c(t) into <directory>/cahn_hilliard_<time, ten decimals>.bin (the reference's Print_Out naming,
+ * cuPentCahnADI.cu:103-140, in raw binary instead of HDF5: "CUSTENC1" | int64 nx | int64 ny | double time | nx*ny
+ * doubles); 0 on success.  custen_cahn_dt: the time step the solver uses. */
+int custen_cahn_write_snapshot(void* solver, const char* directory, double time);
+double custen_cahn_dt(void* solver);
+/* c(t) and c(t - dt) separately (restart from a saved pair of fields); c_old_host NULL: both are c_host */
+void custen_cahn_set_fields(void* solver, const double* c_host, const double* c_old_host);
+
+/* The tolerance-mode solver on y-slabs over several GPUs (BASELINE.json config 5 at 2-8 GPUs; new - the reference is
+ * single-GPU; custen_b200/csrc/cahn_part.cu).  Slab g of `world` owns rows [g n/world, (g+1) n/world) in the grid's own
+ * layout.  Per step a GPU reads from its two neighbours only (a) the 2 + 2 halo rows of c and c(t - dt) for the
+ * right-hand side and (b) the 4 interface values per system of the y-direction partitions next to the seam - no
+ * transposes, no all-to-all; the slabs order themselves with counters in device memory, so steps are enqueued without
+ * host synchronisation and replay from CUDA graphs.  Results are bit-identical to custen_cahn_* with solver 2 on one GPU.
+ *
+ *   one process per GPU   create -> export (a 64-byte cudaIpcMemHandle_t; the caller moves it: MPI, torch.distributed, a
+ *                         file) -> connect(up's handle, down's handle) -> [barrier] -> set_field -> [barrier] -> step ...
+ *   one process, G GPUs   custen_cahn_mg_*: the same slabs, peers reached through cudaDeviceEnablePeerAccess.
+ * create returns NULL when the partitioned layout cannot take the grid: n / world must be a multiple of the partition
+ * height (custen_cahn_set_partition_rows: 32, 64, 128 or 256) and the interface coupling must not reach past the
+ * nearest neighbour. */
 void* custen_cahn_slab_create(int nx, int rank, int world, double D, double gamma, double lx, double dt_over_dx, int device);
-void* custen_cahn_slab_buffer(void* solver, int which);
-void* custen_cahn_slab_handle(void* solver, int which);
-int custen_cahn_slab_current(void* solver);
-void custen_cahn_slab_phase(void* solver, int phase);
-void custen_cahn_slab_set_field(void* solver, const double* rows_host);
-void custen_cahn_slab_get_field(void* solver, double* rows_host);
+void custen_cahn_slab_export(void* slab, void* handle64);
+void custen_cahn_slab_connect(void* slab, const void* up_handle64, const void* down_handle64);
+void custen_cahn_slab_connect_local(void* slab, void* up_slab, void* down_slab);
+void custen_cahn_slab_set_field(void* slab, const double* rows_host);   /* this slab's rows; c(t = 0) = c(t = -dt) */
+void custen_cahn_slab_set_fields(void* slab, const double* c_rows_host, const double* c_old_rows_host);
+void custen_cahn_slab_get_field(void* slab, double* rows_host);          /* synchronises this slab's stream */
+void custen_cahn_slab_step(void* slab, int nsteps);                      /* asynchronous */
+float custen_cahn_slab_time_steps(void* slab, int nsteps);               /* milliseconds (CUDA events on the slab's stream) */
+void custen_cahn_slab_synchronize(void* slab);
+int custen_cahn_slab_error(void* slab);                                  /* neighbour waits that timed out (0 = fine) */
+void custen_cahn_slab_set_timeout(void* slab, double seconds);           /* default 10 s */
+void custen_cahn_slab_set_graph(void* slab, int on);
+int custen_cahn_slab_partition_rows(void* slab);
+void custen_cahn_slab_destroy(void* slab);
+
+void* custen_cahn_mg_create(int nx, int ngpus, const int* devices, double D, double gamma, double lx, double dt_over_dx);
+void custen_cahn_mg_set_field(void* mg, const double* c0_host);         /* whole n x n grid */
+void custen_cahn_mg_get_field(void* mg, double* out_host);
+void custen_cahn_mg_step(void* mg, int nsteps);                         /* asynchronous on every GPU */
+float custen_cahn_mg_time_steps(void* mg, int nsteps);                  /* milliseconds, the slowest GPU */
+int custen_cahn_mg_error(void* mg);
+void custen_cahn_mg_set_graph(void* mg, int on);
+void custen_cahn_mg_destroy(void* mg);
 
 #ifdef __cplusplus
 }

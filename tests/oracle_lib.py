@@ -206,7 +206,12 @@ def ref_cahn_run(c0, nsteps, lx, warm=0):
     return out, ms.value
 
 
-def serial_cahn_run(c0, nsteps, lx, D=1.0, gamma=0.01):
+def serial_cahn_trajectory(c0, stops, lx, D=1.0, gamma=0.01):
+    """serial_cahn_run, returning a copy of the field after each of the (increasing) step counts in `stops`."""
+    return serial_cahn_run(c0, stops[-1], lx, D, gamma, stops=list(stops))
+
+
+def serial_cahn_run(c0, nsteps, lx, D=1.0, gamma=0.01, stops=None):
     """The reference's serial CPU twin, driven function by function in the order of its own main loop
     (serialCahnADI.c:1010-1047) from a caller-supplied field.  Returns the final field, or None if unavailable."""
     lib = serial()
@@ -241,7 +246,8 @@ def serial_cahn_run(c0, nsteps, lx, D=1.0, gamma=0.01):
     w_non = np.array([0, 1, 0, 1, -4, 1, 0, 1, 0], dtype=np.float64) * sig_n
     c_old, c_cur = c0.copy(), c0.copy()
     c_bar, c_half, c_non = np.zeros_like(c0), np.zeros_like(c0), np.zeros_like(c0)
-    for _ in range(nsteps):
+    kept = []
+    for it in range(nsteps):
         lib.findCBar(P(c_old), P(c_cur), P(c_bar), n)
         lib.linearRHS(P(c_bar), P(c_half), P(w_lin), 5, 5, 2, 2, n)
         lib.nonlinearRHS(P(c_cur), P(c_non), P(w_non), 3, 3, 1, 1, n)
@@ -255,7 +261,9 @@ def serial_cahn_run(c0, nsteps, lx, D=1.0, gamma=0.01):
             lib.cyclicInv(P(ds), P(dl), P(diag), P(du), P(dw), P(inv1), P(inv2), P(omega), row, a, b, d, e, m, n)
         lib.transpose(P(c_cur), P(c_half), n)
         lib.findNew(P(c_cur), P(c_bar), P(c_half), n)
-    return c_cur
+        if stops is not None and it + 1 in stops:
+            kept.append(c_cur.copy())
+    return c_cur if stops is None else kept
 
 
 def bits_equal(a, b):

@@ -290,6 +290,33 @@ def test_reference_kernels_at_config2_size():
     assert ol.count_diff(got, ref) == 0
 
 
+@pytest.mark.parametrize("variant,n,tiles,block", [("XYnp", 16384, 4, (32, 32)), ("XYpFun", 16384, 1, (16, 32)),
+                                                   ("XYpFun", 32768, 1, (16, 32))])
+def test_reference_kernels_at_config3_and_config4_sizes(variant, n, tiles, block):
+    """Configs 3 (2d_xy_np, 16384^2, numTiles = 4) and 4 (2d_xy_p_fun, 16384^2 and 32768^2): new engine vs the
+    reference's own kernels (sm_100 rebuild) on the same random grid at the full BASELINE sizes, every double compared
+    bit for bit.  (The reference indexes with int: 32768^2 = 2^30 points still fits.)"""
+    rng = np.random.default_rng(n + tiles)
+    inp = rng.random((n, n))
+    inp *= 2.0
+    inp -= 1.0
+    if variant == "XYnp":
+        coef, kw = cases.weights_cross_xy(2 * np.pi / n, 2 * np.pi / n), dict(H=3, L=1, R=1, V=3, T=1, B=1)
+    else:
+        coef, kw = cases.weights_laplace5(0.25), dict(H=3, L=1, R=1, V=3, T=1, B=1, fun="cubic_xy")
+    ref = np.zeros_like(inp)
+    ref = ol.ref_sweep(variant, inp, ref, coef, tiles=tiles, block=block, **kw)
+    assert ref is not None
+    c = cases._c("cfg34", variant, n, n, tiles, block, coef, **kw)
+    got, path, _ = gu.run_ours(c, inp, out_init=np.zeros_like(inp), return_path=True)
+    assert path.startswith("stream"), path
+    # compare in row blocks: no 8 GiB temporaries
+    diff = 0
+    for r0 in range(0, n, 2048):
+        diff += ol.count_diff(got[r0:r0 + 2048], ref[r0:r0 + 2048])
+    assert diff == 0
+
+
 @pytest.mark.parametrize("variant,nx,ny,kw", [
     ("XYp", 1300, 96, dict(H=3, L=1, R=1, V=3, T=1, B=1)),          # 512 + 512 + 276-column strips, periodic wrap on a partial strip
     ("XYp", 1280, 40, dict(H=5, L=2, R=2, V=5, T=2, B=2)),
