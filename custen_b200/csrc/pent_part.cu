@@ -363,26 +363,37 @@ __device__ __forceinline__ void bulk_s2g(void* dst, unsigned src, unsigned bytes
 }
 
 // The two sweeps of one partition for one system per lane.  at(i) is the lane's i-th unknown in shared memory; the
-// tables are read with broadcast loads.  Rows go through in blocks of R: the loads of block k+1 are issued before the
-// dependent chain of block k (one FMA per row: the term in y_{i-2} and the scaling by 1/d are off the chain), so the
-// chain never waits for shared memory.  CORR: the right-hand side still lacks the x-direction solve's rank-4
-// correction, b_i - (w0 q0_i + w1 q1_i + w2 q2_i + w3 q3_i), applied while the block is staged.
+// tables are read with broadcast loads.  Rows go through in blocks of R with two register sets used alternately: the
+// loads of block k+1 are in flight while the dependent chain of block k runs (one FMA per row: the term in y_{i-2} and
+// the scaling by 1/d are off the chain), and nothing is copied between the sets.  CORR: the right-hand side still
+// lacks the x-direction solve's rank-4 correction, b_i - (w0 q0_i + w1 q1_i + w2 q2_i + w3 q3_i), applied while a
+// block is staged.
+template <int R, bool CORR>
+struct FwdSet
+{
+    double b[R], s[R], l[R], rd[R], q[CORR ? 4 : 1][R];
+};
+template <int R>
+struct BwdSet
+{
+    double y[R], u[R], w[R];
+};
+
 template <int NP, int R, bool CORR, class At>
 __device__ __forceinline__ void sweeps(At at, const double* sF, const double* sB, const double* sQ, const double (&w)[4],
                                        double (&g)[4])
 {
-    static_assert(NP % R == 0 && R % 2 == 0, "block height");
-    double b[R], cs[R], cl[R];
-    auto stage = [&](int i0, double (&raw)[R], double (&rs)[R], double (&rl)[R], double (&rd)[R], double (&q)[CORR ? 4 : 1][R]) {
+    static_assert(NP % (2 * R) == 0 && R % 2 == 0, "block height");
+    auto stage = [&](int i0, FwdSet<R, CORR>& f) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) raw[r] = *at(i0 + r);
+        for (int r = 0; r < R; ++r) f.b[r] = *at(i0 + r);
 #pragma unroll
         for (int r = 0; r < R; ++r)
         {
             const double2 c01 = *reinterpret_cast<const double2*>(sF + 4 * (i0 + r));
-            rs[r] = c01.x;
-            rl[r] = c01.y;
-            rd[r] = sF[4 * (i0 + r) + 2];
+            f.s[r] = c01.x;
+            f.l[r] = c01.y;
+            f.rd[r] = sF[4 * (i0 + r) + 2];
         }
         if (CORR)
         {
@@ -392,98 +403,97 @@ __device__ __forceinline__ void sweeps(At at, const double* sF, const double* sB
                 for (int r = 0; r < R; r += 2)
                 {
                     const double2 v = *reinterpret_cast<const double2*>(sQ + k * NP + i0 + r);
-                    q[k][r] = v.x;
-                    q[k][r + 1] = v.y;
+                    f.q[k][r] = v.x;
+                    f.q[k][r + 1] = v.y;
                 }
         }
     };
-    auto finish = [&](double (&raw)[R], double (&rs)[R], double (&rl)[R], double (&rd)[R], double (&q)[CORR ? 4 : 1][R]) {
+    auto finish = [&](FwdSet<R, CORR>& f) {
 #pragma unroll
         for (int r = 0; r < R; ++r)
         {
-            double v = raw[r];
+            double v = f.b[r];
             if (CORR)
             {
-                double corr = w[0] * q[0][r];
-                corr = fma(w[1], q[1][r], corr);
-                corr = fma(w[2], q[2][r], corr);
-                corr = fma(w[3], q[3][r], corr);
+                double corr = w[0] * f.q[0][r];
+                corr = fma(w[1], f.q[1][r], corr);
+                corr = fma(w[2], f.q[2][r], corr);
+                corr = fma(w[3], f.q[3][r], corr);
                 v -= corr;
             }
-            b[r] = rd[r] * v;
-            cs[r] = rs[r];
-            cl[r] = rl[r];
+            f.b[r] = f.rd[r] * v;
         }
     };
-    {
-        double raw[R], rs[R], rl[R], rd[R], q[CORR ? 4 : 1][R];
-        stage(0, raw, rs, rl, rd, q);
-        finish(raw, rs, rl, rd, q);
-    }
     // forward: y_i = b_i / d_i - s'_i y_{i-2} - l'_i y_{i-1}
     double y2 = 0.0, y1 = 0.0;
-#pragma unroll 1
-    for (int i0 = 0; i0 < NP; i0 += R)
-    {
-        double raw[R], rs[R], rl[R], rd[R], q[CORR ? 4 : 1][R];
-        const bool more = i0 + R < NP;
-        if (more) stage(i0 + R, raw, rs, rl, rd, q);
+    auto chain = [&](int i0, const FwdSet<R, CORR>& f) {
 #pragma unroll
         for (int r = 0; r < R; ++r)
         {
-            const double t = fma(cs[r], y2, b[r]);
-            const double v = fma(cl[r], y1, t);
+            const double t = fma(f.s[r], y2, f.b[r]);
+            const double v = fma(f.l[r], y1, t);
             *at(i0 + r) = v;
             y2 = y1;
             y1 = v;
         }
-        if (more) finish(raw, rs, rl, rd, q);
+    };
+    {
+        FwdSet<R, CORR> A, B;
+        stage(0, A);
+        finish(A);
+#pragma unroll 1
+        for (int i0 = 0; i0 < NP; i0 += 2 * R)
+        {
+            stage(i0 + R, B);
+            chain(i0, A);
+            finish(B);
+            const bool more = i0 + 2 * R < NP;
+            if (more) stage(i0 + 2 * R, A);
+            chain(i0 + R, B);
+            if (more) finish(A);
+        }
     }
     // backward: x_i = y_i - w_i x_{i+2} - u_i x_{i+1}
     double x1 = 0.0, x2 = 0.0;
-    double yb[R], cu[R], cw[R];
-    auto stage_b = [&](int i0, double (&ry)[R], double (&ru)[R], double (&rw)[R]) {
+    auto stage_b = [&](int i0, BwdSet<R>& f) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) ry[r] = *at(i0 + r);
+        for (int r = 0; r < R; ++r) f.y[r] = *at(i0 + r);
 #pragma unroll
         for (int r = 0; r < R; ++r)
         {
             const double2 c = *reinterpret_cast<const double2*>(sB + 2 * (i0 + r));
-            ru[r] = c.x;
-            rw[r] = c.y;
+            f.u[r] = c.x;
+            f.w[r] = c.y;
         }
     };
-    stage_b(NP - R, yb, cu, cw);
-#pragma unroll 1
-    for (int i0 = NP - R; i0 >= 0; i0 -= R)
-    {
-        double ry[R], ru[R], rw[R];
-        const bool more = i0 > 0;
-        if (more) stage_b(i0 - R, ry, ru, rw);
+    auto chain_b = [&](int i0, const BwdSet<R>& f) {
 #pragma unroll
         for (int r = R - 1; r >= 0; --r)
         {
-            const double t = fma(cw[r], x2, yb[r]);
-            const double v = fma(cu[r], x1, t);
+            const double t = fma(f.w[r], x2, f.y[r]);
+            const double v = fma(f.u[r], x1, t);
             *at(i0 + r) = v;
             x2 = x1;
             x1 = v;
-            if (i0 + r == NP - 1) g[3] = v;
-            if (i0 + r == NP - 2) g[2] = v;
         }
-        if (more)
+    };
+    {
+        BwdSet<R> A, B;
+        stage_b(NP - R, A);
+#pragma unroll 1
+        for (int i0 = NP - R; i0 >= 0; i0 -= 2 * R)
         {
-#pragma unroll
-            for (int r = 0; r < R; ++r)
-            {
-                yb[r] = ry[r];
-                cu[r] = ru[r];
-                cw[r] = rw[r];
-            }
+            stage_b(i0 - R, B);
+            chain_b(i0, A);
+            const bool more = i0 - 2 * R >= 0;
+            if (more) stage_b(i0 - 2 * R, A);
+            chain_b(i0 - R, B);
         }
     }
     g[0] = x1;
     g[1] = x2;
+    g[2] = *at(NP - 2);
+    g[3] = *at(NP - 1);
 }
 
 // Unknowns along the rows of the array, systems contiguous (the y-direction solve on data[row][sys]).  One warp = one
@@ -596,21 +606,29 @@ __global__ void __launch_bounds__(32) k_part_cols(double* __restrict__ data, int
 }
 
 // q_p = sum_j Q_j gamma_{p+j} for this rank's partitions.  gptr[r] = rank r's interface array (P_loc x 4 x nsys), in peer
-// memory for r != rank; one thread per (system, local partition).
-__global__ void k_spike_reduce(const double* const* __restrict__ gptr, int rank, int P_loc, int P_tot, int nsys,
-                               const double* __restrict__ Q, const int* __restrict__ joff, int nb, double* __restrict__ q)
+// memory for r != rank; one thread per (system, local partition).  The coupling blocks sit in shared memory; the
+// interface values of four blocks are requested before the first of them is used.
+constexpr int RED_MAXB = 64;   // coupling blocks held in shared memory (more: the rest is read from global memory)
+__global__ void __launch_bounds__(128) k_spike_reduce(const double* const* __restrict__ gptr, int rank, int P_loc, int P_tot,
+                                                      int nsys, const double* __restrict__ Q, const int* __restrict__ joff, int nb,
+                                                      double* __restrict__ q)
 {
-    const int sys = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ double sQ[RED_MAXB * 16];
+    __shared__ const double* sG[RED_MAXB];   // where block b's interface values start for this CTA's partition
     const int pl = blockIdx.y;
-    if (sys >= nsys) return;
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int b = 0; b < nb; ++b)
+    const int nbs = nb < RED_MAXB ? nb : RED_MAXB;
+    for (int e = threadIdx.x; e < nbs * 16; e += blockDim.x) sQ[e] = Q[e];
+    for (int b = threadIdx.x; b < nb && b < RED_MAXB; b += blockDim.x)
     {
         int pg = (rank * P_loc + pl + joff[b]) % P_tot;
         if (pg < 0) pg += P_tot;
-        const double* g = gptr[pg / P_loc] + ((size_t)(pg % P_loc) * 4) * nsys + sys;
-        const double g0 = g[0], g1 = g[(size_t)nsys], g2 = g[(size_t)2 * nsys], g3 = g[(size_t)3 * nsys];
-        const double* Qb = Q + 16 * b;
+        sG[b] = gptr[pg / P_loc] + ((size_t)(pg % P_loc) * 4) * nsys;
+    }
+    __syncthreads();
+    const int sys = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sys >= nsys) return;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    auto add = [&](const double* Qb, double g0, double g1, double g2, double g3) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
         {
@@ -619,6 +637,32 @@ __global__ void k_spike_reduce(const double* const* __restrict__ gptr, int rank,
             acc[k] = fma(Qb[4 * k + 2], g2, acc[k]);
             acc[k] = fma(Qb[4 * k + 3], g3, acc[k]);
         }
+    };
+    int b = 0;
+    for (; b + 4 <= nbs; b += 4)
+    {
+        double gv[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+        {
+            const double* g = sG[b + j] + sys;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) gv[j][k] = g[(size_t)k * nsys];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) add(sQ + 16 * (b + j), gv[j][0], gv[j][1], gv[j][2], gv[j][3]);
+    }
+    for (; b < nbs; ++b)
+    {
+        const double* g = sG[b] + sys;
+        add(sQ + 16 * b, g[0], g[(size_t)nsys], g[(size_t)2 * nsys], g[(size_t)3 * nsys]);
+    }
+    for (; b < nb; ++b)   // beyond the shared-memory table
+    {
+        int pg = (rank * P_loc + pl + joff[b]) % P_tot;
+        if (pg < 0) pg += P_tot;
+        const double* g = gptr[pg / P_loc] + ((size_t)(pg % P_loc) * 4) * nsys + sys;
+        add(Q + 16 * b, g[0], g[(size_t)nsys], g[(size_t)2 * nsys], g[(size_t)3 * nsys]);
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) q[((size_t)pl * 4 + k) * nsys + sys] = acc[k];
