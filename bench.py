@@ -323,6 +323,56 @@ def variant_table(cs, torch, n, steps, warmup, peak):
     return table
 
 
+def cahn_on_slabs(cs, torch, dist, rank, world, local_rank, n=4096, steps=40, check_steps=4):
+    """Config 5 on `world` GPUs (custen_cahn_slab_*: no collective on the data path, NCCL only moves IPC handles).
+    Parity inside the run: every rank also steps the whole grid with the single-GPU solver on its own GPU and compares
+    its slab's rows bit for bit (partitions are solved with the same arithmetic wherever they live); rank 0 adds the
+    distance of that road from the bit-identical one (= the reference's GPU solver, tests/test_cahn_gpu.py)."""
+    from custen_b200.cahn import CahnHilliard, CahnHilliardSlab
+    rows = n // world
+    c0 = np.random.default_rng(0).uniform(-0.1, 0.1, (n, n))
+    mine = c0[rank * rows:(rank + 1) * rows]
+    slab = CahnHilliardSlab(n, device=local_rank)
+    slab.set_field(mine)
+    slab.step(check_steps)
+    got = slab.field()
+    single = CahnHilliard(n, device=local_rank, solver=2)
+    single.set_field(c0)
+    single.step(check_steps)
+    whole = single.field()
+    single.destroy()
+    torch.cuda.set_device(local_rank)
+    differing = int(np.count_nonzero(got.view(np.int64) != whole[rank * rows:(rank + 1) * rows].view(np.int64)))
+    rel = None
+    if rank == 0:
+        exact = CahnHilliard(n, device=local_rank, solver=0)
+        exact.set_field(c0)
+        exact.step(check_steps)
+        ref = exact.field()
+        exact.destroy()
+        torch.cuda.set_device(local_rank)
+        rel = float(np.max(np.abs(whole - ref)) / np.max(np.abs(ref)))
+    slab.set_field(mine)
+    slab.step(5)
+    slab.synchronize()
+    dist.barrier()
+    ms = slab.time_steps(steps)
+    t = torch.tensor([ms, float(differing), float(slab.error())], device="cuda", dtype=torch.float64)
+    tmax = t.clone()
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    slab.destroy()
+    ms = float(tmax[0].item())
+    return {"n_gpus": world, "ms_per_step": round(ms, 4), "mpoint_steps_per_s": round(n * n / ms / 1e3, 1), "solver": 2,
+            "steps_timed": steps, "timing": "CUDA events on every slab's stream, max over ranks",
+            "parity": {"bits_differing_vs_single_gpu": int(t[1].item()), "neighbour_wait_timeouts": int(t[2].item()),
+                       "steps_compared": check_steps, "rel_vs_bit_identical_road": rel},
+            "exchange": "per step and GPU: 2 x 2 halo rows of c and c(t - dt) and the 4 interface values per system of "
+                        "the y-partitions within reach of the seam, read in place over NVLink; no all-to-all",
+            "note": "tolerance-mode road (custen_b200/csrc/cahn_part.cu); the distance to the bit-identical road at 4096^2 is "
+                    "the reference solver's own rounding error (tests/test_pent_part_cpu.py)"}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import custen_b200 as cs
@@ -536,6 +586,14 @@ def run_ours(args, rank, world, local_rank):
             lib.custen_host_free(h_in)
             lib.custen_host_free(h_out)
 
+    # ---- BASELINE.json config 5 at N > 1: the Cahn-Hilliard step on y-slabs (every rank takes part) ---------------
+    cahn_slabs = None
+    if world > 1 and not args.no_cahn:
+        try:
+            cahn_slabs = cahn_on_slabs(cs, torch, dist, rank, world, local_rank)
+        except Exception as ex:   # noqa: BLE001 - a bench line with the error is worth more than no line
+            cahn_slabs = {"error": repr(ex)}
+
     if rank != 0:
         if dist:
             dist.destroy_process_group()
@@ -544,6 +602,8 @@ def run_ours(args, rank, world, local_rank):
     # ---- rank 0 extras: per-variant table, other configs, cpu baseline -----------------------------------------
     torch.cuda.empty_cache()
     extras = {}
+    if cahn_slabs is not None:
+        extras["cahn_hilliard_4096"] = cahn_slabs
     if world == 1 and not args.no_table:
         extras["variants_16384"] = variant_table(cs, torch, 16384, 10, 3, peak)
         for wname in ("x_p_8192", "xy_np_16384_t4"):
@@ -626,9 +686,19 @@ def run_ours(args, rank, world, local_rank):
                     res["solver"] = sol.solver
                 sol.destroy()
             res["mpoint_steps_per_s"] = round(ncahn * ncahn / res["ms_per_step"] / 1e3, 1)
+            fields = []
+            for solver in (2, 0):
+                sol = CahnHilliard(ncahn, device=local_rank, solver=solver)
+                sol.set_field(np.random.default_rng(0).uniform(-0.1, 0.1, (ncahn, ncahn)))
+                sol.step(4)
+                fields.append(sol.field())
+                sol.destroy()
+            res["parity"] = {"steps_compared": 4, "rel_vs_bit_identical_road": float(
+                np.max(np.abs(fields[0] - fields[1])) / np.max(np.abs(fields[1])))}
             res["note"] = ("custen_cahn_step: right-hand side (2 stencils) + 2 cyclic pentadiagonal ADI solves per step; "
-                           "solver 2 = partitioned solve, <= 1e-13 relative to the reference GPU solver; the other two "
-                           "roads are bit-identical to it (tests/test_cahn_gpu.py)")
+                           "solver 2 = partitioned solve (per step within 1e-13 of the reference GPU solver up to n = 1024 "
+                           "and within the reference solver's own rounding error beyond); the other two roads are "
+                           "bit-identical to the reference (tests/test_cahn_gpu.py)")
             extras[f"cahn_hilliard_{ncahn}"] = res
 
     cpu = None
@@ -715,6 +785,7 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the seam rows after the timed loop")
     ap.add_argument("--no-table", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-cahn", action="store_true", help="skip the Cahn-Hilliard (config 5) measurement at N > 1")
     ap.add_argument("--no-serial", action="store_true", help="skip the ~30 s serial CPU Cahn-Hilliard baseline (config 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)

@@ -45,7 +45,7 @@ EXPORTED = (
        "custen_cahn_slab_synchronize", "custen_cahn_slab_error", "custen_cahn_slab_set_timeout", "custen_cahn_slab_set_graph",
        "custen_cahn_slab_partition_rows", "custen_cahn_slab_destroy", "custen_cahn_mg_create", "custen_cahn_mg_set_field",
        "custen_cahn_mg_get_field", "custen_cahn_mg_step", "custen_cahn_mg_time_steps", "custen_cahn_mg_error",
-       "custen_cahn_mg_set_graph", "custen_cahn_mg_destroy", "custen_cahn_set_fields", "custen_cahn_write_snapshot", "custen_cahn_dt",
+       "custen_cahn_mg_set_graph", "custen_cahn_mg_destroy", "custen_cahn_set_fields", "custen_cahn_write_snapshot", "custen_cahn_dt", "custen_cahn_set_rhs_stream",
        "custen_set_handle_managed_policy", "custen_mem_advise", "custen_mem_prefetch", "custen_fill_hash",
        "custen_slab_create", "custen_slab_export", "custen_slab_connect", "custen_slab_field", "custen_slab_rows",
        "custen_slab_compute", "custen_slab_swap", "custen_slab_run", "custen_slab_run_plain", "custen_slab_time_run",
@@ -144,6 +144,7 @@ def load():
     lib.custen_cahn_set_fields.argtypes, lib.custen_cahn_set_fields.restype = [_c_void_p] * 3, None
     lib.custen_cahn_write_snapshot.argtypes = [_c_void_p, ctypes.c_char_p, ctypes.c_double]
     lib.custen_cahn_write_snapshot.restype = _c_int
+    lib.custen_cahn_set_rhs_stream.argtypes, lib.custen_cahn_set_rhs_stream.restype = [_c_int], None
     lib.custen_cahn_dt.argtypes, lib.custen_cahn_dt.restype = [_c_void_p], ctypes.c_double
     lib.custen_cahn_slab_set_field.argtypes, lib.custen_cahn_slab_set_field.restype = [_c_void_p, _c_void_p], None
     lib.custen_cahn_slab_get_field.argtypes, lib.custen_cahn_slab_get_field.restype = [_c_void_p, _c_void_p], None

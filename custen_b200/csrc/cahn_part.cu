@@ -25,7 +25,7 @@
 
 #include "../../include/cuSten.h"
 #include "../../include/custen_c.h"
-#include "cahn_rhs.cuh"
+#include "cahn_rhs_stream.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -36,6 +36,8 @@
 namespace custen_cahn {
 
 static void ck(const char* what) { checkError(what); }
+
+static int g_rhs_stream = 1;   // default for slabs created from now on (custen_cahn_set_rhs_stream)
 
 // ---- kernels -------------------------------------------------------------------------------------------------------------
 
@@ -151,6 +153,7 @@ struct PartSlab
     cudaStream_t stream;
     cudaGraphExec_t gexec;
     int gexec_cur, use_graph;
+    int rhs_stream;            // 1: row-streaming right-hand side (k_rhs_stream), 0: the tile kernel (k_rhs_fused)
     cudaEvent_t ev0, ev1;
 };
 
@@ -250,6 +253,8 @@ PartSlab* part_slab_create(int n, int rank, int world, double D, double gamma, d
     cudaEventCreate(&s->ev0);
     cudaEventCreate(&s->ev1);
     s->use_graph = 1;
+    s->rhs_stream = g_rhs_stream;
+    cudaFuncSetAttribute(k_rhs_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM);
     cudaDeviceSynchronize();
     ck("cahn slab: create");
     return s;
@@ -296,8 +301,16 @@ static void enqueue_step(PartSlab* s)
         halo.o_down = (const double*)(s->down_block + old_off);
         k_wait<<<1, 32, 0, st>>>(s->flags, F_FIELD_UP, 0);
     }
-    dim3 tg(n / 32, rows / 32);
-    k_rhs_fused<false><<<tg, 128, 0, st>>>(cOld, c, halo, s->work, n, rows, s->rc);
+    if (s->rhs_stream)
+    {
+        dim3 sg((n + RS_W - 1) / RS_W, rows / RS_BR);
+        k_rhs_stream<<<sg, RS_NT + 32, RS_SMEM, st>>>(cOld, c, halo, s->work, n, rows, s->rc);
+    }
+    else
+    {
+        dim3 tg(n / 32, rows / 32);
+        k_rhs_fused<false><<<tg, 128, 0, st>>>(cOld, c, halo, s->work, n, rows, s->rc);
+    }
     part_solve_cols(s->plan, s->work, rows, n, s->Gx, st);
     part_reduce(s->plan, s->gptr_x, 1, 0, s->P, rows, s->qx, st);
     part_solve_rows(s->plan, s->work, n, rows, s->Gy, s->qx, rows, st);
@@ -520,10 +533,14 @@ struct MultiGpu
 
 namespace custen_cahn {
 void part_set_default_np(int np) { g_np_default = np > 0 ? np : 128; }
+void part_set_rhs_stream(int on) { g_rhs_stream = on; }
 int part_default_np() { return g_np_default; }
 }  // namespace custen_cahn
 
 extern "C" {
+
+// tuning / tests: 1 (default) the row-streaming right-hand-side kernel, 0 the tile kernel; for solvers created afterwards
+void custen_cahn_set_rhs_stream(int on) { part_set_rhs_stream(on); }
 
 // One y-slab of the tolerance-mode solver per process / GPU.  Returns NULL when the partitioned layout cannot take the
 // grid (n / world not a multiple of the partition height 32 / 64 / 128 / 256, or the interface coupling would reach

@@ -34,6 +34,7 @@ cudaStream_t part_slab_stream(PartSlab* s);
 void part_slab_destroy(PartSlab* s);
 
 void part_set_default_np(int np);
+void part_set_rhs_stream(int on);
 int part_default_np();
 
 }  // namespace custen_cahn

@@ -174,7 +174,6 @@ __global__ void __launch_bounds__(128, 6) k_rhs_fused(const double* __restrict__
     }
 }
 
-
 }  // namespace custen_cahn
 
 #endif

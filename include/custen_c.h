@@ -231,6 +231,7 @@ int custen_pent_part_choose_np(int n, int wanted);
 /* The same systems through the DEVICE kernels: layout 0 rhs[sys * n + i], 1 rhs[i * nsys + sys], 2 the ADI pair on an
  * n x n array (along x, then along y); bit-identical to custen_pent_part_host per system. */
 int custen_pent_part_device(int n, int np, const double* coef5, int nsys, const double* rhs_host, double* x_host, int layout);
+void custen_cahn_set_rhs_stream(int on);                        /* tuning / tests, solver 2: 1 row-streaming right-hand side (default), 0 tile kernel */
 void custen_cahn_set_table_rows(int rows);                      /* tuning / tests: coefficient rows staged per refill */
 
 /* Snapshot of c(t) into <directory>/cahn_hilliard_<time, ten decimals>.bin (the reference's Print_Out naming,

@@ -355,3 +355,19 @@ def test_snapshots_and_analysis_of_the_rehosted_driver(tmp_path):
     assert abs(rows[-1][0] - 450 * dt) < 1e-9
     assert all(np.isfinite(r[1]) and r[1] > 1.0 for r in rows) and rows[-1][1] > rows[0][1]
     assert rows[-1][2] > rows[0][2] > 0.0
+
+
+@pytest.mark.parametrize("n", [64, 128, 320, 544, 1024, 1184, 2048])
+def test_row_streaming_right_hand_side_matches_the_tile_kernel(n):
+    """k_rhs_stream (producer warp + ring of rows, zero weights skipped) against k_rhs_fused: same bits, including
+    strips narrower than 512 columns and a partial last strip."""
+    import custen_b200 as cs
+    c0 = _initial(n, seed=n + 3)
+    cs.load().custen_cahn_set_rhs_stream(0)
+    try:
+        want = _ours(c0, 5, solver=2)
+    finally:
+        cs.load().custen_cahn_set_rhs_stream(1)
+    got = _ours(c0, 5, solver=2)
+    assert np.isfinite(got).all()
+    assert ol.count_diff(got, want) == 0

@@ -31,12 +31,12 @@ def _initial(n, seed=0):
     return np.random.default_rng(seed).uniform(-0.1, 0.1, size=(n, n))
 
 
-def _single(c0, steps, np_rows=None):
+def _single(c0, steps, np_rows=None, device=0):
     import custen_b200 as cs
     if np_rows:
         cs.load().custen_cahn_set_partition_rows(np_rows)
     try:
-        s = CahnHilliard(c0.shape[0], solver=2)
+        s = CahnHilliard(c0.shape[0], solver=2, device=device)
         assert s.solver == 2
         s.set_field(c0)
         s.step(steps)
@@ -109,7 +109,8 @@ def _worker(rank, world, port, n, steps, q):
         from custen_b200.cahn import CahnHilliardSlab
         c0 = _initial(n, seed=11)
         rows = n // world
-        want = _single(c0, steps)[rank * rows:(rank + 1) * rows]
+        want = _single(c0, steps, device=rank)[rank * rows:(rank + 1) * rows]
+        torch.cuda.set_device(rank)
         slab = CahnHilliardSlab(n)
         slab.set_field(c0[rank * rows:(rank + 1) * rows])
         slab.step(steps)
@@ -133,7 +134,7 @@ def test_one_process_per_gpu_over_cuda_ipc(n, steps):
     for p in procs:
         p.start()
     for p in procs:
-        p.join(timeout=240)
+        p.join(timeout=120)
         assert p.exitcode == 0
     res = dict(q.get(timeout=5) for _ in range(world))
     assert res == {r: 0 for r in range(world)}
