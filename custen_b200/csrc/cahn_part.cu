@@ -304,7 +304,7 @@ static void enqueue_step(PartSlab* s)
     if (s->rhs_stream)
     {
         dim3 sg((n + RS_W - 1) / RS_W, rows / RS_BR);
-        k_rhs_stream<<<sg, RS_NT + 32, RS_SMEM, st>>>(cOld, c, halo, s->work, n, rows, s->rc);
+        k_rhs_stream<<<sg, RS_NT, RS_SMEM, st>>>(cOld, c, halo, s->work, n, rows, s->rc);
     }
     else
     {

@@ -9,9 +9,9 @@ namespace custen_cahn {
 // ---- the same right-hand side as a row-streaming kernel (tolerance-mode road) -----------------------------------------------
 // k_rhs_fused spends its time on instruction issue and shared-memory traffic (ncu: 80 M warp instructions for 16.8 M
 // points, 67 % of the shared-memory wavefront peak, FP64 pipe 40 %).  Here a CTA owns a strip of 512 columns x 32 rows and
-// streams the 36 rows it needs through a ring in shared memory: a producer warp moves rows of c and cOld in with the
-// async proxy (bulk copies on mbarriers, the periodic wrap / the neighbouring slabs' halo rows resolved per row), and
-// each of 128 consumer threads owns 4 columns and marches down the rows with its 5-row window of cBar and 3-row window
+// streams the 36 rows it needs through a ring in shared memory: rows of c and cOld are moved in with the async proxy
+// (bulk copies on mbarriers issued by warp 0 a few stages ahead, the periodic wrap / the neighbouring slabs' halo rows
+// resolved per row), and each of the 128 threads owns 4 columns and marches down the rows with its 5-row window of cBar and 3-row window
 // of (c^3 - c) in registers - nothing is staged twice, nothing is exchanged between threads.  The zero weights of the
 // two stencils (13 of 25 and 5 of 9 taps are non-zero: cuPentCahnADI.cu:452-476, :164-188) are skipped, which leaves
 // every partial sum as it was: fma(0, v, acc) == acc for finite v.  Per point: 27 FP64 operations, 2 shared-memory
@@ -48,7 +48,7 @@ __device__ __forceinline__ void g2s(unsigned dst, const double* src, unsigned by
 }
 }  // namespace rs
 
-__global__ void __launch_bounds__(RS_NT + 32) k_rhs_stream(const double* __restrict__ cOld, const double* __restrict__ cCurr,
+__global__ void __launch_bounds__(RS_NT, 2) k_rhs_stream(const double* __restrict__ cOld, const double* __restrict__ cCurr,
                                                              const RhsHalo halo, double* __restrict__ out, int n, int rows,
                                                              const RhsCoef k)
 {
@@ -69,51 +69,51 @@ __global__ void __launch_bounds__(RS_NT + 32) k_rhs_stream(const double* __restr
     }
     __syncthreads();
 
-    if (tid >= RS_NT)
-    {
-        // ---- producer warp: lane = (row of the stage, array, piece) ----
-        const int lane = tid - RS_NT;
-        const int r = lane / 6, which = lane % 6, arr = which / 3, piece = which % 3;   // piece 0 body, 1 left halo, 2 right halo
-        const unsigned bytes_stage = (unsigned)RS_SR * 2u * (unsigned)(ws + 4) * 8u;
-        for (int f = 0; f < RS_ROWS / RS_SR; ++f)
+    // ---- filling the ring: warp 0, between its own rows; lane = (row of the stage, array, piece) ----
+    // (a fifth, dedicated producer warp would cost a whole CTA of occupancy: registers are handed out four warps at a time)
+    const int lane = tid & 31, warp = tid >> 5;
+    auto fill = [&](int f) {
+        const int slot = f % RS_NS;
+        const unsigned full = rs::saddr(bars + slot), empty = rs::saddr(bars + RS_NS + slot);
+        if (f >= RS_NS) rs::bar_wait(empty, (unsigned)((f / RS_NS - 1) & 1));
+        if (lane == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"((unsigned)RS_SR * 2u * (unsigned)(ws + 4) * 8u)
+                         : "memory");
+        __syncwarp();
+        if (lane < RS_SR * 6)
         {
-            const int slot = f % RS_NS;
-            const unsigned full = rs::saddr(bars + slot), empty = rs::saddr(bars + RS_NS + slot);
-            if (f >= RS_NS) rs::bar_wait(empty, (unsigned)((f / RS_NS - 1) & 1));
-            if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(bytes_stage) : "memory");
-            __syncwarp();
-            if (lane < RS_SR * 6)
+            const int r = lane / 6, which = lane % 6, arr = which / 3, piece = which % 3;   // piece 0 body, 1 left halo, 2 right halo
+            int gy = y0 - 2 + f * RS_SR + r;
+            const double* base = arr ? cOld : cCurr;
+            if (gy < 0 || gy >= rows)
             {
-                int gy = y0 - 2 + f * RS_SR + r;
-                const double* base = arr ? cOld : cCurr;
-                if (gy < 0 || gy >= rows)
+                if (halo.c_up != nullptr)
                 {
-                    if (halo.c_up != nullptr)
-                    {
-                        const bool up = gy < 0;
-                        base = up ? (arr ? halo.o_up : halo.c_up) : (arr ? halo.o_down : halo.c_down);
-                        gy = up ? gy + 2 : gy - rows;
-                    }
-                    else
-                        gy = gy < 0 ? gy + rows : gy - rows;
+                    const bool up = gy < 0;
+                    base = up ? (arr ? halo.o_up : halo.c_up) : (arr ? halo.o_down : halo.c_down);
+                    gy = up ? gy + 2 : gy - rows;
                 }
-                const double* grow = base + (size_t)gy * n;
-                double* srow = ring + slot * RS_STAGE_DOUBLES + (size_t)(r * 2 + arr) * RS_PW;
-                if (piece == 0)
-                    rs::g2s(rs::saddr(srow + 2), grow + xs, (unsigned)ws * 8u, full);
-                else if (piece == 1)
-                    rs::g2s(rs::saddr(srow), grow + (xs == 0 ? n - 2 : xs - 2), 16u, full);
                 else
-                    rs::g2s(rs::saddr(srow + 2 + ws), grow + (xs + ws >= n ? 0 : xs + ws), 16u, full);
+                    gy = gy < 0 ? gy + rows : gy - rows;
             }
+            const double* grow = base + (size_t)gy * n;
+            double* srow = ring + slot * RS_STAGE_DOUBLES + (size_t)(r * 2 + arr) * RS_PW;
+            if (piece == 0)
+                rs::g2s(rs::saddr(srow + 2), grow + xs, (unsigned)ws * 8u, full);
+            else if (piece == 1)
+                rs::g2s(rs::saddr(srow), grow + (xs == 0 ? n - 2 : xs - 2), 16u, full);
+            else
+                rs::g2s(rs::saddr(srow + 2 + ws), grow + (xs + ws >= n ? 0 : xs + ws), 16u, full);
         }
-        return;
-    }
+        __syncwarp();
+    };
+    constexpr int NFILL = RS_ROWS / RS_SR;
+    if (warp == 0)
+        for (int f = 0; f < RS_NS && f < NFILL; ++f) fill(f);
 
     // ---- consumers ----
     const int x0 = 4 * tid;
     const bool active = x0 < ws;
-    const int lane = tid & 31;
     // row kk of the stream is grid row y0 - 2 + kk; output row y0 + j needs cBar rows j .. j + 4, (c^3 - c) rows j + 1 ..
     // j + 3 and c - cOld of row j + 2, so it is computed when row kk = j + 4 has arrived
     double B[5][8] = {};   // cBar rows kk - 4 .. kk, columns x0 - 2 .. x0 + 5
@@ -123,7 +123,12 @@ __global__ void __launch_bounds__(RS_NT + 32) k_rhs_stream(const double* __restr
     for (int kk = 0; kk < RS_ROWS; ++kk)
     {
         const int f = kk / RS_SR, slot = f % RS_NS;
-        if (kk % RS_SR == 0) rs::bar_wait(rs::saddr(bars + slot), (unsigned)((f / RS_NS) & 1));
+        if (kk % RS_SR == 0)
+        {
+            // the slot of the stage this warp has just left is refilled with the stage NS - 1 ahead of the current one
+            if (warp == 0 && f >= 1 && f - 1 + RS_NS < NFILL) fill(f - 1 + RS_NS);
+            rs::bar_wait(rs::saddr(bars + slot), (unsigned)((f / RS_NS) & 1));
+        }
         if (active)
         {
             const double* srow = ring + slot * RS_STAGE_DOUBLES + (size_t)((kk % RS_SR) * 2) * RS_PW + x0;

@@ -183,25 +183,31 @@ def ref_weno(inp, u, v, dx, dy, tiles=1, block=(32, 32), out_init=None):
     return out
 
 
-_cahn_ref = None
 
 
-def ref_cahn_run(c0, nsteps, lx, warm=0):
+_cahn_libs = {}
+
+
+def ref_cahn_run(c0, nsteps, lx, warm=0, engine="reference"):
     """The reference's GPU Cahn-Hilliard solver (timing twin + BatchHyper + cuPentBatch, oracle/ref_cahn_shim.cu):
-    returns (final field after warm + nsteps steps, ms per timed step)."""
-    global _cahn_ref
-    if _cahn_ref is None:
-        path = _ensure_built("libcahn_ref.so")
+    returns (final field after warm + nsteps steps, ms per timed step).
+    engine = "reference": linked against the reference's own cuSten library (libcahn_ref.so, the oracle);
+    engine = "new": the SAME translation units linked against this repo's libcuSten.a (libcahn_new.so) - the
+    zero-source-change drop-in proof for config 5."""
+    if engine not in _cahn_libs:
+        path = _ensure_built("libcahn_ref.so" if engine == "reference" else "libcahn_new.so")
         if path is None:
             return None
-        _cahn_ref = ctypes.CDLL(path)
-        _cahn_ref.ref_cahn_run2.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, _dp, _dp, _dp]
-        _cahn_ref.ref_cahn_run2.restype = ctypes.c_int
+        lib = ctypes.CDLL(path)
+        lib.ref_cahn_run2.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, _dp, _dp, _dp]
+        lib.ref_cahn_run2.restype = ctypes.c_int
+        _cahn_libs[engine] = lib
+    lib = _cahn_libs[engine]
     c0 = np.ascontiguousarray(c0, dtype=np.float64)
     n = c0.shape[0]
     out = np.empty_like(c0)
     ms = ctypes.c_double(0.0)
-    rc = _cahn_ref.ref_cahn_run2(n, warm, nsteps, lx, c0.ctypes.data_as(_dp), out.ctypes.data_as(_dp), ctypes.byref(ms))
+    rc = lib.ref_cahn_run2(n, warm, nsteps, lx, c0.ctypes.data_as(_dp), out.ctypes.data_as(_dp), ctypes.byref(ms))
     assert rc == 0
     return out, ms.value
 

@@ -1,7 +1,7 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_cahn_gpu.py tests/test_cahn_slab_gpu.py -q -m gpu > gpurun_out/r2j_tests.log 2>&1; echo "rc=$?" >> gpurun_out/r2j_tests.log
-grep -n "^E   \|passed\|failed\|^FAILED" gpurun_out/r2j_tests.log | cut -c1-300 | head -40
-for np in 64 128; do python tools/cahn_steps.py 4096 40 2 $np; done 2>&1 | tee gpurun_out/r2j_cahn_time.log
-python tools/cahn_steps.py 512 200 2 2>&1 | tee -a gpurun_out/r2j_cahn_time.log
-ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/r2j_launches_cahn4096.csv python tools/cahn_steps.py 4096 3 2 128 > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_rhs_stream -s 4 -c 1 -o gpurun_out/r2j_k_rhs_stream -f python tools/cahn_steps.py 4096 3 2 128 > /dev/null 2>&1
+free -g | head -2
+timeout 1500 python -m pytest tests -q -m gpu -x --durations=8 > gpurun_out/r2l_tests.log 2>&1; echo "rc=$?" >> gpurun_out/r2l_tests.log
+grep -n "^E   \|passed\|failed\|^FAILED\|s call\|s setup" gpurun_out/r2l_tests.log | cut -c1-250 | head -40
+timeout 300 python -m pytest tests/test_dropin_examples_gpu.py -q -m gpu -s -k cahn_hilliard_driver 2>&1 | grep "config 5" | tee gpurun_out/r2l_dropin_cfg5.log
+timeout 900 python bench.py > gpurun_out/r2l_bench_n1.json 2> gpurun_out/r2l_bench_n1.err; echo "bench rc=$?"
+tail -c 600 gpurun_out/r2l_bench_n1.err
