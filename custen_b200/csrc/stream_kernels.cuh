@@ -622,57 +622,90 @@ __device__ __forceinline__ double weno_pow2(double xd)
     if (ax >= 8.6736174e-19f && ax <= 1.1529215e18f) return (double)pow2_core(x);   // 2^-60 .. 2^60
     return (double)weno_pow2_library(x);
 }
+#define CUSTEN_WENO5_BODY(POW2)                                                                                  \
+    const double epsilon = 1e-06;                                                                                \
+    const double phi1 = (1.0 / 3.0) * v1 - (7.0 / 6.0) * v2 + (11.0 / 6.0) * v3;                                 \
+    const double phi2 = -(1.0 / 6.0) * v2 + (5.0 / 6.0) * v3 + (1.0 / 3.0) * v4;                                 \
+    const double phi3 = (1.0 / 3.0) * v3 + (5.0 / 6.0) * v4 - (1.0 / 6.0) * v5;                                  \
+    const double s1 = (13.0 / 12.0) * POW2(v1 - 2.0 * v2 + v3) + 0.25 * POW2(v1 - 4.0 * v2 + 3.0 * v3);          \
+    const double s2 = (13.0 / 12.0) * POW2(v2 - 2.0 * v3 + v4) + 0.25 * POW2(v2 - v4);                           \
+    const double s3 = (13.0 / 12.0) * POW2(v3 - 2.0 * v4 + v5) + 0.25 * POW2(3.0 * v3 - 4.0 * v4 + v5);          \
+    const double alpha1 = 0.1 / POW2(s1 + epsilon);                                                              \
+    const double alpha2 = 0.6 / POW2(s2 + epsilon);                                                              \
+    const double alpha3 = 0.3 / POW2(s3 + epsilon);                                                              \
+    const double denom = 1.0 / (alpha1 + alpha2 + alpha3);                                                       \
+    const double w1 = alpha1 * denom;                                                                            \
+    const double w2 = alpha2 * denom;                                                                            \
+    const double w3 = alpha3 * denom;                                                                            \
+    return phi1 * w1 + phi2 * w2 + phi3 * w3;
+
+// the nine powf of one reconstruction, each with its own range test and library call: the road for windows that hold
+// an argument outside the verified range (exact zeros in flat regions, NaN, overflow)
+static __device__ __noinline__ double weno5_checked(double v1, double v2, double v3, double v4, double v5)
+{
+    CUSTEN_WENO5_BODY(weno_pow2)
+}
+// The main road runs the nine restated powf with no branch between them (so the compiler interleaves the
+// independent chains; a call-or-core branch per powf left every chain alone in its basic block) and keeps the
+// smallest and largest |argument| seen, as integers (NaN sorts above infinity).  One test at the end sends the
+// rare window with an argument outside the verified range through weno5_checked.
+struct WenoRange
+{
+    uint32_t lo = 0x7fffffffu, hi = 0u;
+    __device__ __forceinline__ double pow2(double xd)
+    {
+        const float x = (float)xd;
+        const uint32_t bits = __float_as_uint(x) & 0x7fffffffu;
+        lo = min(lo, bits);
+        hi = max(hi, bits);
+        return (double)pow2_core(x);
+    }
+    __device__ __forceinline__ bool verified() const { return lo >= 0x21800000u && hi <= 0x5d800000u; }  // 2^-60, 2^60
+};
+__device__ __forceinline__ double weno5_unchecked(WenoRange& rg, double v1, double v2, double v3, double v4, double v5)
+{
+    CUSTEN_WENO5_BODY(rg.pow2)
+}
 __device__ __forceinline__ double weno5(double v1, double v2, double v3, double v4, double v5)
 {
-    const double epsilon = 1e-06;
-    const double phi1 = (1.0 / 3.0) * v1 - (7.0 / 6.0) * v2 + (11.0 / 6.0) * v3;
-    const double phi2 = -(1.0 / 6.0) * v2 + (5.0 / 6.0) * v3 + (1.0 / 3.0) * v4;
-    const double phi3 = (1.0 / 3.0) * v3 + (5.0 / 6.0) * v4 - (1.0 / 6.0) * v5;
-    const double s1 = (13.0 / 12.0) * weno_pow2(v1 - 2.0 * v2 + v3) + 0.25 * weno_pow2(v1 - 4.0 * v2 + 3.0 * v3);
-    const double s2 = (13.0 / 12.0) * weno_pow2(v2 - 2.0 * v3 + v4) + 0.25 * weno_pow2(v2 - v4);
-    const double s3 = (13.0 / 12.0) * weno_pow2(v3 - 2.0 * v4 + v5) + 0.25 * weno_pow2(3.0 * v3 - 4.0 * v4 + v5);
-    const double alpha1 = 0.1 / weno_pow2(s1 + epsilon);
-    const double alpha2 = 0.6 / weno_pow2(s2 + epsilon);
-    const double alpha3 = 0.3 / weno_pow2(s3 + epsilon);
-    const double denom = 1.0 / (alpha1 + alpha2 + alpha3);
-    const double w1 = alpha1 * denom;
-    const double w2 = alpha2 * denom;
-    const double w3 = alpha3 * denom;
-    return phi1 * w1 + phi2 * w2 + phi3 * w3;
+    WenoRange rg;
+    const double r = weno5_unchecked(rg, v1, v2, v3, v4, v5);
+    if (rg.verified()) return r;
+    return weno5_checked(v1, v2, v3, v4, v5);
 }
-// one-sided differences along a line through the centre; `c` = centre index, `st` = element stride of the line
+// one-sided differences along a line through the centre; `c` = centre index, `st` = element stride of the line.
+// The six first differences around the centre are formed once and the upwind side picks five of them
+// (reference: two branches with five differences each, 2d_xyADVWENO_p_kernel.cu:283-390 - same operands, same
+// operations, no divergence when the velocity changes sign inside a warp).
 __device__ __forceinline__ double weno_line(const double* a, int c, int st, double vel, double coe)
 {
-    double v1, v2, v3, v4, v5;
-    if (vel > 0.0)
-    {
-        v1 = (a[c - 2 * st] - a[c - 3 * st]) * coe;
-        v2 = (a[c - st] - a[c - 2 * st]) * coe;
-        v3 = (a[c] - a[c - st]) * coe;
-        v4 = (a[c + st] - a[c]) * coe;
-        v5 = (a[c + 2 * st] - a[c + st]) * coe;
-    }
-    else
-    {
-        v5 = (a[c - st] - a[c - 2 * st]) * coe;
-        v4 = (a[c] - a[c - st]) * coe;
-        v3 = (a[c + st] - a[c]) * coe;
-        v2 = (a[c + 2 * st] - a[c + st]) * coe;
-        v1 = (a[c + 3 * st] - a[c + 2 * st]) * coe;
-    }
-    return weno5(v1, v2, v3, v4, v5);
+    const double a0 = a[c - 3 * st], a1 = a[c - 2 * st], a2 = a[c - st], a3 = a[c], a4 = a[c + st], a5 = a[c + 2 * st],
+                 a6 = a[c + 3 * st];
+    const double d0 = (a1 - a0) * coe, d1 = (a2 - a1) * coe, d2 = (a3 - a2) * coe, d3 = (a4 - a3) * coe,
+                 d4 = (a5 - a4) * coe, d5 = (a6 - a5) * coe;
+    const bool pos = vel > 0.0;
+    return weno5(pos ? d0 : d5, pos ? d1 : d4, pos ? d2 : d3, pos ? d3 : d2, pos ? d4 : d1);
 }
 struct OpWeno
 {
-    static __device__ __forceinline__ double apply(const Band& b, double* buf, double* cf, int tl, int PW, ptrdiff_t gidx)
+    // The streaming kernel walks a thread's rows in a rolled loop for this operator (one point is ~1300 instructions:
+    // unrolled eight times the body overflowed the instruction cache) and fetches the next row's velocities from
+    // global memory before it starts on the current row.
+    static constexpr bool kRowLoop = true;
+    static __device__ __forceinline__ double apply_uv(const Band& b, const double* buf, int tl, int PW, double u, double v)
     {
         const int c = tl + 3 * PW + 3;  // centre of the 7 x 7 window
-        const double u = b.aux0[gidx], v = b.aux1[gidx];
         const double Fx = weno_line(buf, c, 1, u, b.p0);
         const double Fy = weno_line(buf, c, PW, v, b.p1);
         return u * Fx + v * Fy;
     }
+    static __device__ __forceinline__ double apply(const Band& b, double* buf, double* cf, int tl, int PW, ptrdiff_t gidx)
+    {
+        return apply_uv(b, buf, tl, PW, b.aux0[gidx], b.aux1[gidx]);
+    }
 };
+template <class Op, class = void> struct op_row_loop { static constexpr bool value = false; };
+template <class Op> struct op_row_loop<Op, decltype((void)Op::kRowLoop)> { static constexpr bool value = true; };
 
 template <int NT, int SR, int NS, int MINB, class Op>
 __global__ void __launch_bounds__(NT + 32, MINB) stream_tile_kernel(const __grid_constant__ StreamArgs a)
@@ -721,7 +754,31 @@ __global__ void __launch_bounds__(NT + 32, MINB) stream_tile_kernel(const __grid
         {
             double* o = b.out + (ptrdiff_t)ybase * b.nx + gx;
             const int tl0 = t + dlt;  // top-left of the window of stage row 0 (buffer row i <-> input row yo - T)
-            if (i_lo == 0 && i_hi == SR)
+            if constexpr (op_row_loop<Op>::value)
+            {
+                if (i_lo < i_hi)
+                {
+                    const double* pu = b.aux0 + (ptrdiff_t)(ybase + i_lo) * b.nx + gx;
+                    const double* pv = b.aux1 + (ptrdiff_t)(ybase + i_lo) * b.nx + gx;
+                    double u = *pu, v = *pv;
+#pragma unroll 1
+                    for (int i = i_lo; i < i_hi; ++i)
+                    {
+                        double un = u, vn = v;
+                        if (i + 1 < i_hi)
+                        {
+                            pu += b.nx;
+                            pv += b.nx;
+                            un = *pu;
+                            vn = *pv;
+                        }
+                        o[(ptrdiff_t)i * b.nx] = Op::apply_uv(b, buf, tl0 + i * PW, PW, u, v);
+                        u = un;
+                        v = vn;
+                    }
+                }
+            }
+            else if (i_lo == 0 && i_hi == SR)
             {
 #pragma unroll
                 for (int i = 0; i < SR; ++i)
@@ -762,6 +819,10 @@ struct TileSmall { static constexpr int NT = 256, SR = 8, NS = 3, MAXCPS = 2; };
 struct TileBig { static constexpr int NT = 512, SR = 16, NS = 3, MAXCPS = 1; };
 // WENO is compute-bound (18 single-precision powf per point): as many warps as the register file allows.
 struct TileWeno { static constexpr int NT = 736, SR = 8, NS = 2, MAXCPS = 1; };
+struct TileWeno1 { static constexpr int NT = 480, SR = 8, NS = 2, MAXCPS = 1; };
+struct TileWeno2 { static constexpr int NT = 352, SR = 8, NS = 2, MAXCPS = 2; };
+struct TileWeno3 { static constexpr int NT = 224, SR = 8, NS = 2, MAXCPS = 3; };
+struct TileWeno4 { static constexpr int NT = 608, SR = 8, NS = 2, MAXCPS = 1; };
 
 struct LaunchGeom
 {
@@ -797,7 +858,8 @@ inline void launch_tile_geom(StreamArgs& a, cudaStream_t st)
 }
 
 // Opaque user functions: their register need is only known at device link, where a kernel compiled for a large CTA
-// (a low per-thread register cap) would fail to link against a register-hungry callee.  So the opaque road stays on
+// (a low per-thread register cap) would fail to link against a register-hungry callee (tried: with a 72-register
+// cap nvlink refuses the library's own weighted_xy fixture, which ptxas gave 94 registers).  So the opaque road stays on
 // 288-thread CTAs (cap 224 registers) and takes as many of them per SM as the occupancy calculator allows.
 struct TileOpq256 { static constexpr int NT = 256, SR = 8, NS = 3, MAXCPS = 3; };
 

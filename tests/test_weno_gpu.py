@@ -71,6 +71,32 @@ def test_bit_exact_against_reference_weno_kernel(nx, ny, tiles):
     assert ol.count_diff(got_m, ref) == 0
 
 
+def test_windows_outside_the_verified_powf_range_match_the_reference_kernel():
+    """Flat and linear regions (exact-zero smoothness arguments), huge and tiny amplitudes, an infinity and a NaN:
+    the windows whose powf arguments leave the range in which the restated powf was verified take the library call."""
+    nx, ny = 512, 256
+    phi, u, v = _fields(nx, ny, seed=3)
+    phi[:64, :] = 0.75                                    # flat: every difference is exactly zero
+    phi[64:96, :] = np.arange(nx)[None, :] * 0.125        # linear in x with exactly representable steps
+    phi[96:128, :] = np.arange(32)[:, None] * 0.5         # linear in y
+    phi[128:160, :128] *= 1e30                            # (float) of the second differences overflows 2^60
+    phi[128:160, 128:256] *= 1e-30                        # ... and underflows 2^-60
+    phi[128:160, 256:384] *= 1e200                        # infinite after the conversion to float
+    phi[200, 100] = np.inf
+    phi[220, 300] = np.nan
+    dx, dy = 2 * np.pi / nx, 2 * np.pi / ny
+    with np.errstate(all="ignore"):
+        ref = ol.ref_weno(phi, u, v, dx, dy, tiles=2, block=(32, 16))
+        got, path = _ours(phi, u, v, dx, dy, tiles=2)
+    assert path == "stream_tile"
+    nan_r, nan_g = np.isnan(ref), np.isnan(got)
+    assert (nan_r == nan_g).all() and nan_r.any()
+    assert ol.count_diff(np.where(nan_g, 0.0, got), np.where(nan_r, 0.0, ref)) == 0
+    got_fb, path = _ours(phi, u, v, dx, dy, tiles=2, fallback=True)
+    assert path == "fallback" and (np.isnan(got_fb) == nan_r).all()
+    assert ol.count_diff(np.where(nan_r, 0.0, got_fb), np.where(nan_r, 0.0, ref)) == 0
+
+
 def test_cpu_oracle_agrees_to_single_precision():
     nx, ny = 128, 96
     phi, u, v = _fields(nx, ny, seed=5)

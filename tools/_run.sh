@@ -1,7 +1,3 @@
 mkdir -p gpurun_out
-free -g | head -2
-timeout 1500 python -m pytest tests -q -m gpu -x --durations=8 > gpurun_out/r2l_tests.log 2>&1; echo "rc=$?" >> gpurun_out/r2l_tests.log
-grep -n "^E   \|passed\|failed\|^FAILED\|s call\|s setup" gpurun_out/r2l_tests.log | cut -c1-250 | head -40
-timeout 300 python -m pytest tests/test_dropin_examples_gpu.py -q -m gpu -s -k cahn_hilliard_driver 2>&1 | grep "config 5" | tee gpurun_out/r2l_dropin_cfg5.log
-timeout 900 python bench.py > gpurun_out/r2l_bench_n1.json 2> gpurun_out/r2l_bench_n1.err; echo "bench rc=$?"
-tail -c 600 gpurun_out/r2l_bench_n1.err
+timeout 600 python -m pytest tests/test_weno_gpu.py tests/test_parity_gpu.py -q -m gpu -x -k "weno or opaque" 2>&1 | tail -5
+for g in 0 1 2 3 4; do for f in random example; do CUSTEN_WENO_GEOM=$g timeout 120 python tools/weno_time.py 16384 $f; done; done 2>&1 | grep WENO | tee gpurun_out/r2n_weno_geom.log
