@@ -17,6 +17,7 @@
 #define CUSTEN_B200_STREAM_KERNELS_CUH
 
 #include "engine.h"
+#include "weno_op.cuh"
 
 namespace custen {
 
@@ -530,162 +531,6 @@ struct OpInlineXY
     }
 };
 
-// Fifth-order WENO advection u dphi/dx + v dphi/dy, upwinded per point (13th public variant).  The expressions are
-// those of the reference (2d_xyADVWENO_p_kernel.cu:51-86, :283-390; notation of Osher & Fedkiw, Level Set Methods),
-// including its use of the single-precision powf on double arguments, so that results match it bit for bit.
-//
-// powf(x, 2.0f) is NOT x * x (it differs for 3.2 % of all float inputs: profiles/r2_weno_pow_probe.log) and it is the
-// kernel's whole cost - 18 calls per point.  What libdevice computes on its main path is restated below as the PTX nvcc
-// emits for the call (CUDA 12.9), minus the special-case handling (x == 1, NaN, denormal scaling, overflow /
-// underflow, 0 and inf).  tools/weno_pow_probe.cu compared it with powf over all 2^32 float bit patterns on a B200:
-// identical for every input with 2^-60 <= |x| <= 2^60.  Inside that range the restated path is used, outside it
-// the library call.
-__device__ __forceinline__ float pow2_core(float x)
-{
-    float out;
-    asm("{\n"
-        ".reg .f32 f<66>;\n"
-        ".reg .b32 r<16>;\n"
-        ".reg .pred p4;\n"
-        "abs.f32 f2, %1;\n"
-        "mov.b32 r5, f2;\n"
-        "add.s32 r6, r5, -1060439283;\n"
-        "and.b32 r7, r6, -8388608;\n"
-        "sub.s32 r8, r5, r7;\n"
-        "mov.b32 f10, r8;\n"
-        "cvt.rn.f32.s32 f11, r7;\n"
-        "mov.f32 f12, 0f00000000;\n"
-        "fma.rn.f32 f13, f11, 0f34000000, f12;\n"
-        "add.f32 f14, f10, 0fBF800000;\n"
-        "add.f32 f15, f10, 0f3F800000;\n"
-        "rcp.approx.ftz.f32 f16, f15;\n"
-        "add.f32 f17, f14, f14;\n"
-        "mul.f32 f18, f17, f16;\n"
-        "mul.f32 f19, f18, f18;\n"
-        "neg.f32 f20, f18;\n"
-        "sub.f32 f21, f14, f18;\n"
-        "add.f32 f22, f21, f21;\n"
-        "fma.rn.f32 f23, f20, f14, f22;\n"
-        "mul.rn.f32 f24, f16, f23;\n"
-        "fma.rn.f32 f25, f19, 0f3A2C32E4, 0f3B52E7DB;\n"
-        "fma.rn.f32 f26, f25, f19, 0f3C93BB73;\n"
-        "fma.rn.f32 f27, f26, f19, 0f3DF6384F;\n"
-        "mul.rn.f32 f28, f27, f19;\n"
-        "fma.rn.f32 f29, f18, 0f3FB8AA3B, f13;\n"
-        "mul.f32 f30, f28, 0f40400000;\n"
-        "sub.f32 f31, f13, f29;\n"
-        "fma.rn.f32 f32, f18, 0f3FB8AA3B, f31;\n"
-        "fma.rn.f32 f33, f24, 0f3FB8AA3B, f32;\n"
-        "fma.rn.f32 f34, f18, 0f32A55E34, f33;\n"
-        "fma.rn.f32 f35, f30, f24, f34;\n"
-        "fma.rn.f32 f36, f28, f18, f35;\n"
-        "add.rn.f32 f37, f29, f36;\n"
-        "mov.f32 f38, 0f40000000;\n"
-        "mul.rn.f32 f39, f37, f38;\n"
-        "cvt.rni.f32.f32 f40, f39;\n"
-        "sub.f32 f41, f39, f40;\n"
-        "neg.f32 f42, f39;\n"
-        "fma.rn.f32 f43, f37, 0f40000000, f42;\n"
-        "neg.f32 f44, f29;\n"
-        "add.rn.f32 f45, f37, f44;\n"
-        "neg.f32 f46, f45;\n"
-        "add.rn.f32 f47, f36, f46;\n"
-        "fma.rn.f32 f48, f47, 0f40000000, f43;\n"
-        "add.f32 f49, f41, f48;\n"
-        "setp.gt.f32 p4, f40, 0f00000000;\n"
-        "selp.b32 r9, 0, -2097152000, p4;\n"
-        "cvt.rzi.s32.f32 r10, f40;\n"
-        "shl.b32 r11, r10, 23;\n"
-        "sub.s32 r12, r11, r9;\n"
-        "mov.b32 f52, r12;\n"
-        "add.s32 r13, r9, 2130706432;\n"
-        "mov.b32 f53, r13;\n"
-        "fma.rn.f32 f54, f49, 0f391FCB8E, 0f3AAF85ED;\n"
-        "fma.rn.f32 f55, f54, f49, 0f3C1D9856;\n"
-        "fma.rn.f32 f56, f55, f49, 0f3D6357BB;\n"
-        "fma.rn.f32 f57, f56, f49, 0f3E75FDEC;\n"
-        "fma.rn.f32 f58, f57, f49, 0f3F317218;\n"
-        "fma.rn.f32 f59, f58, f49, 0f3F800000;\n"
-        "mul.f32 f60, f59, f53;\n"
-        "mul.f32 %0, f60, f52;\n"
-        "}\n"
-        : "=f"(out)
-        : "f"(x));
-    return out;
-}
-
-static __device__ __noinline__ float weno_pow2_library(float x) { return powf(x, 2.0f); }
-__device__ __forceinline__ double weno_pow2(double xd)
-{
-    const float x = (float)xd;   // the reference passes doubles to powf(float, float): same conversion
-    const float ax = fabsf(x);
-    if (ax >= 8.6736174e-19f && ax <= 1.1529215e18f) return (double)pow2_core(x);   // 2^-60 .. 2^60
-    return (double)weno_pow2_library(x);
-}
-#define CUSTEN_WENO5_BODY(POW2)                                                                                  \
-    const double epsilon = 1e-06;                                                                                \
-    const double phi1 = (1.0 / 3.0) * v1 - (7.0 / 6.0) * v2 + (11.0 / 6.0) * v3;                                 \
-    const double phi2 = -(1.0 / 6.0) * v2 + (5.0 / 6.0) * v3 + (1.0 / 3.0) * v4;                                 \
-    const double phi3 = (1.0 / 3.0) * v3 + (5.0 / 6.0) * v4 - (1.0 / 6.0) * v5;                                  \
-    const double s1 = (13.0 / 12.0) * POW2(v1 - 2.0 * v2 + v3) + 0.25 * POW2(v1 - 4.0 * v2 + 3.0 * v3);          \
-    const double s2 = (13.0 / 12.0) * POW2(v2 - 2.0 * v3 + v4) + 0.25 * POW2(v2 - v4);                           \
-    const double s3 = (13.0 / 12.0) * POW2(v3 - 2.0 * v4 + v5) + 0.25 * POW2(3.0 * v3 - 4.0 * v4 + v5);          \
-    const double alpha1 = 0.1 / POW2(s1 + epsilon);                                                              \
-    const double alpha2 = 0.6 / POW2(s2 + epsilon);                                                              \
-    const double alpha3 = 0.3 / POW2(s3 + epsilon);                                                              \
-    const double denom = 1.0 / (alpha1 + alpha2 + alpha3);                                                       \
-    const double w1 = alpha1 * denom;                                                                            \
-    const double w2 = alpha2 * denom;                                                                            \
-    const double w3 = alpha3 * denom;                                                                            \
-    return phi1 * w1 + phi2 * w2 + phi3 * w3;
-
-// the nine powf of one reconstruction, each with its own range test and library call: the road for windows that hold
-// an argument outside the verified range (exact zeros in flat regions, NaN, overflow)
-static __device__ __noinline__ double weno5_checked(double v1, double v2, double v3, double v4, double v5)
-{
-    CUSTEN_WENO5_BODY(weno_pow2)
-}
-// The main road runs the nine restated powf with no branch between them (so the compiler interleaves the
-// independent chains; a call-or-core branch per powf left every chain alone in its basic block) and keeps the
-// smallest and largest |argument| seen, as integers (NaN sorts above infinity).  One test at the end sends the
-// rare window with an argument outside the verified range through weno5_checked.
-struct WenoRange
-{
-    uint32_t lo = 0x7fffffffu, hi = 0u;
-    __device__ __forceinline__ double pow2(double xd)
-    {
-        const float x = (float)xd;
-        const uint32_t bits = __float_as_uint(x) & 0x7fffffffu;
-        lo = min(lo, bits);
-        hi = max(hi, bits);
-        return (double)pow2_core(x);
-    }
-    __device__ __forceinline__ bool verified() const { return lo >= 0x21800000u && hi <= 0x5d800000u; }  // 2^-60, 2^60
-};
-__device__ __forceinline__ double weno5_unchecked(WenoRange& rg, double v1, double v2, double v3, double v4, double v5)
-{
-    CUSTEN_WENO5_BODY(rg.pow2)
-}
-__device__ __forceinline__ double weno5(double v1, double v2, double v3, double v4, double v5)
-{
-    WenoRange rg;
-    const double r = weno5_unchecked(rg, v1, v2, v3, v4, v5);
-    if (rg.verified()) return r;
-    return weno5_checked(v1, v2, v3, v4, v5);
-}
-// one-sided differences along a line through the centre; `c` = centre index, `st` = element stride of the line.
-// The six first differences around the centre are formed once and the upwind side picks five of them
-// (reference: two branches with five differences each, 2d_xyADVWENO_p_kernel.cu:283-390 - same operands, same
-// operations, no divergence when the velocity changes sign inside a warp).
-__device__ __forceinline__ double weno_line(const double* a, int c, int st, double vel, double coe)
-{
-    const double a0 = a[c - 3 * st], a1 = a[c - 2 * st], a2 = a[c - st], a3 = a[c], a4 = a[c + st], a5 = a[c + 2 * st],
-                 a6 = a[c + 3 * st];
-    const double d0 = (a1 - a0) * coe, d1 = (a2 - a1) * coe, d2 = (a3 - a2) * coe, d3 = (a4 - a3) * coe,
-                 d4 = (a5 - a4) * coe, d5 = (a6 - a5) * coe;
-    const bool pos = vel > 0.0;
-    return weno5(pos ? d0 : d5, pos ? d1 : d4, pos ? d2 : d3, pos ? d3 : d2, pos ? d4 : d1);
-}
 struct OpWeno
 {
     // The streaming kernel walks a thread's rows in a rolled loop for this operator (one point is ~1300 instructions:
