@@ -163,6 +163,11 @@ struct StreamArgs
     int nstrips, nchunks, chunk_rows, nitems;
     int stage_doubles;  // (PFX + SR) * PW
     int edge_last;      // slab time stepping: the first and last row chunk (the ones that touch halo rows) are swept last
+    int warp_carry;     // tile family: who moves the PFX rows in front of a stage over from the previous stage.  1 = the
+                        // producer warp, and the consumer warps hand a stage back one by one (no block-wide barrier: short
+                        // windows, PFX <= SR / 4, and the compute-bound WENO operator); 0 = all consumers together behind a
+                        // block-wide barrier (tall windows, where one warp is too slow: 9-row windows ran at 294 instead of
+                        // 394 Gpoints/s with the producer copying)
 };
 
 // Order in which a CTA walks the row chunks.  In slab mode the two chunks that need a neighbour's rows come last, so
@@ -265,6 +270,9 @@ __device__ __forceinline__ void producer_loop(const StreamArgs& a, unsigned char
 
             const int r = r0 + lane;
             const bool live = lane < nrows && band_row_exists(b, r);
+            // warp_carry: the PFX rows in front of the stage are the last rows of the previous stage, copied over by this
+            // warp (not for the first stage of an item, whose first PFX windows produce no output)
+            const bool carry = a.warp_carry && a.PFX > 0 && r0 != in_lo;
             const uint32_t total = __reduce_add_sync(0xffffffffu, live ? row_bytes : 0u);
 
             const uint32_t bar = full0 + 8 * s;
@@ -290,20 +298,39 @@ __device__ __forceinline__ void producer_loop(const StreamArgs& a, unsigned char
                 if (lw) bulk_g2s(dst, src + (b.nx - lw), (uint32_t)lw * 8u, bar);
                 if (rw) bulk_g2s(dst + (uint32_t)(b.nx - u0) * 8u, src, (uint32_t)rw * 8u, bar);
             }
+            if (a.warp_carry)
+            {
+                // The stage's barrier takes two arrivals in this mode: the one above (with the byte count of the bulk
+                // copies) and this one, after the carry rows are in place.  The previous stage (always a full one) must
+                // have landed before its last PFX rows are read; its slot cannot be refilled under the copy, the
+                // refill being issued by this same warp later.
+                if (carry)
+                {
+                    const int sp = s == 0 ? NS - 1 : s - 1;
+                    mbar_wait(full0 + 8 * sp, s == 0 ? ph ^ 1 : ph);
+                    const double2* src = reinterpret_cast<const double2*>(smem + SMEM_STAGE_OFF + (size_t)sp * stage_bytes +
+                                                                          (size_t)SR * pitch_bytes);
+                    double2* dst2 = reinterpret_cast<double2*>(smem + SMEM_STAGE_OFF + (size_t)s * stage_bytes);
+                    const int n2 = a.PFX * a.PW / 2;
+                    for (int e = lane; e < n2; e += 32) dst2[e] = src[e];
+                    __syncwarp();
+                }
+                if (lane == 0) mbar_arrive(bar);
+            }
             if (++s == NS) { s = 0; ph ^= 1; }
         }
     }
 }
 
 template <int NS>
-__device__ __forceinline__ void stream_prologue(unsigned char* smem, int consumer_arrivals)
+__device__ __forceinline__ void stream_prologue(unsigned char* smem, int consumer_arrivals, int producer_arrivals = 1)
 {
     if (threadIdx.x == 0)
     {
         const uint32_t full0 = smem_u32(smem + SMEM_BAR_OFF);
         for (int i = 0; i < NS; ++i)
         {
-            mbar_init(full0 + 8 * i, 1);
+            mbar_init(full0 + 8 * i, producer_arrivals);
             mbar_init(full0 + 8 * (NS + i), consumer_arrivals);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -556,7 +583,7 @@ template <int NT, int SR, int NS, int MINB, class Op>
 __global__ void __launch_bounds__(NT + 32, MINB) stream_tile_kernel(const __grid_constant__ StreamArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    stream_prologue<NS>(smem, 1);
+    stream_prologue<NS>(smem, a.warp_carry ? NT / 32 : 1, a.warp_carry ? 2 : 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == NT / 32)
@@ -641,16 +668,25 @@ __global__ void __launch_bounds__(NT + 32, MINB) stream_tile_kernel(const __grid
             for (int i = i_lo; i < i_hi; ++i) o[(ptrdiff_t)i * b.nx] = 0.0;
         }
 
-        // carry the last V-1 rows over to the front of the next stage
-        if (PFX > 0)
+        if (a.warp_carry)
         {
-            const int sn = (s + 1 == NS) ? 0 : s + 1;
-            double* nxt = stage0 + (size_t)sn * a.stage_doubles;
-            const double* src = buf + d.nrows * PW;
-            for (int e = t; e < PFX * PW; e += NT) nxt[e] = src[e];
+            // the producer warp moves the carry rows: every consumer warp hands the stage back on its own
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + 8 * s);
         }
-        consumer_bar(NT);
-        if (t == 0) mbar_arrive(empty0 + 8 * s);
+        else
+        {
+            // carry the last V-1 rows over to the front of the next stage
+            if (PFX > 0)
+            {
+                const int sn = (s + 1 == NS) ? 0 : s + 1;
+                double* nxt = stage0 + (size_t)sn * a.stage_doubles;
+                const double* src = buf + d.nrows * PW;
+                for (int e = t; e < PFX * PW; e += NT) nxt[e] = src[e];
+            }
+            consumer_bar(NT);
+            if (t == 0) mbar_arrive(empty0 + 8 * s);
+        }
         if (++s == NS) { s = 0; ph ^= 1; }
     }
     slab_epilogue(b, NT);
@@ -662,12 +698,9 @@ __global__ void __launch_bounds__(NT + 32, MINB) stream_tile_kernel(const __grid
 // windows, 256-column strips and two CTAs per SM otherwise.
 struct TileSmall { static constexpr int NT = 256, SR = 8, NS = 3, MAXCPS = 2; };
 struct TileBig { static constexpr int NT = 512, SR = 16, NS = 3, MAXCPS = 1; };
-// WENO is compute-bound (18 single-precision powf per point): as many warps as the register file allows.
+// WENO is compute-bound (18 single-precision powf per point): as many warps as the register file allows
+// (480 / 608-thread CTAs and two or three smaller CTAs per SM measured within 3 % or slower: profiles/r2_weno_geom_v2.log).
 struct TileWeno { static constexpr int NT = 736, SR = 8, NS = 2, MAXCPS = 1; };
-struct TileWeno1 { static constexpr int NT = 480, SR = 8, NS = 2, MAXCPS = 1; };
-struct TileWeno2 { static constexpr int NT = 352, SR = 8, NS = 2, MAXCPS = 2; };
-struct TileWeno3 { static constexpr int NT = 224, SR = 8, NS = 2, MAXCPS = 3; };
-struct TileWeno4 { static constexpr int NT = 608, SR = 8, NS = 2, MAXCPS = 1; };
 
 struct LaunchGeom
 {
@@ -689,6 +722,7 @@ inline size_t tile_geometry(StreamArgs& a)
     a.PW = a.Lp + a.TW + a.Rp;
     a.nstrips = (a.b.nx + a.TW - 1) / a.TW;
     a.PFX = a.b.V - 1;
+    a.warp_carry = (a.PFX * 4 <= G::SR || a.b.weno) ? 1 : 0;
     a.stage_doubles = (a.PFX + G::SR) * a.PW;
     return SMEM_STAGE_OFF + (size_t)G::NS * a.stage_doubles * sizeof(double);
 }

@@ -1,5 +1,9 @@
 mkdir -p gpurun_out
-tools/weno_pow_probe.bin | tee gpurun_out/r2o_weno_pow_probe.log
-timeout 600 python -m pytest tests/test_weno_gpu.py -q -m gpu -x 2>&1 | tail -5
-for g in 0 1 4; do for f in random example; do CUSTEN_WENO_GEOM=$g timeout 120 python tools/weno_time.py 16384 $f; done; done 2>&1 | grep WENO | tee gpurun_out/r2o_weno_geom.log
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:stream_tile -c 1 -s 3 -o gpurun_out/r2o_weno python tools/weno_time.py 4096 example > gpurun_out/r2o_weno_ncu.log 2>&1; tail -2 gpurun_out/r2o_weno_ncu.log
+CUSTEN_TILE_RELOAD=2 timeout 200 compute-sanitizer --tool memcheck python tools/weno_time.py 1024 example 2>&1 | grep -v "^=========     at\|^=========     by\|Host Frame" | head -20
+timeout 900 python -m pytest tests/test_parity_gpu.py tests/test_weno_gpu.py tests/test_slab_c_gpu.py -q -m gpu -x 2>&1 | tail -4
+for r in 0 2; do
+CUSTEN_TILE_RELOAD=$r timeout 200 python tools/fun_time.py 16384
+CUSTEN_TILE_RELOAD=$r timeout 200 python tools/fun_time.py 32768
+CUSTEN_TILE_RELOAD=$r timeout 120 python tools/weno_time.py 16384 example
+CUSTEN_TILE_RELOAD=$r timeout 120 python tools/weno_time.py 16384 random
+done 2>&1 | grep "WENO\|fun" | tee gpurun_out/r2q_reload.log

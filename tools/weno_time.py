@@ -35,5 +35,5 @@ for _ in range(10):
 lib.custen_event_record(e1, hp, 0)
 lib.custen_event_synchronize(e1)
 ms = lib.custen_event_elapsed_ms(e0, e1) / 10
-print("WENO", n, field, os.environ.get("CUSTEN_WENO_GEOM", "0"), "ms", ms, "Gpt/s", n * n / ms / 1e6, cs.last_path(h))
+print("WENO", n, field, "ms", ms, "Gpt/s", n * n / ms / 1e6, cs.last_path(h))
 cs.cuStenDestroy2DXYWENOADVp(h)
