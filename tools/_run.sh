@@ -1,9 +1,18 @@
 mkdir -p gpurun_out
-CUSTEN_TILE_RELOAD=2 timeout 200 compute-sanitizer --tool memcheck python tools/weno_time.py 1024 example 2>&1 | grep -v "^=========     at\|^=========     by\|Host Frame" | head -20
-timeout 900 python -m pytest tests/test_parity_gpu.py tests/test_weno_gpu.py tests/test_slab_c_gpu.py -q -m gpu -x 2>&1 | tail -4
-for r in 0 2; do
-CUSTEN_TILE_RELOAD=$r timeout 200 python tools/fun_time.py 16384
-CUSTEN_TILE_RELOAD=$r timeout 200 python tools/fun_time.py 32768
-CUSTEN_TILE_RELOAD=$r timeout 120 python tools/weno_time.py 16384 example
-CUSTEN_TILE_RELOAD=$r timeout 120 python tools/weno_time.py 16384 random
-done 2>&1 | grep "WENO\|fun" | tee gpurun_out/r2q_reload.log
+nvidia-smi -L | wc -l
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 8 --steps 20 --warmup 3 > gpurun_out/r2r_bench_n8.json 2> gpurun_out/r2r_bench_n8.err; echo "bench rc=$?"
+tail -c 400 gpurun_out/r2r_bench_n8.err
+python - <<'P'
+import json
+d=json.loads(open('gpurun_out/r2r_bench_n8.json').read().strip().splitlines()[-1])
+print(d['value'], d['ms_per_step'], d['roofline']['frac'], d['e2e']['value'], d['e2e']['link_frac'], d['parity'])
+print(d.get('cahn_hilliard_4096'))
+print(d.get('halo_exchange'))
+P
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29534 bench.py --gpus 4 --steps 20 --warmup 3 --no-e2e > gpurun_out/r2r_bench_n4.json 2> gpurun_out/r2r_bench_n4.err; echo "bench4 rc=$?"
+python - <<'P'
+import json
+d=json.loads(open('gpurun_out/r2r_bench_n4.json').read().strip().splitlines()[-1])
+print(d['value'], d['ms_per_step'], d['roofline']['frac'], d['parity'])
+print(d.get('cahn_hilliard_4096'))
+P
