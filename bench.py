@@ -153,7 +153,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(index)], stdout=subprocess.PIPE, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -161,18 +161,19 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t_from=None, t_to=None):
+        """Summary of the samples taken in [t_from, t_to] (perf_counter seconds; default: all of them)."""
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
         self.proc.terminate()
         self.th.join(timeout=2)
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        rows = [r for t, r in self.rows if (t_from is None or t >= t_from) and (t_to is None or t <= t_to)]
+        sm = [float(r[0]) for r in rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in rows)]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
 
@@ -422,13 +423,14 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
+    sampler = ClockSampler(local_rank)   # started ahead of the warm-up: nvidia-smi needs a moment to deliver its first line
     ss.run(args.warmup)
     ss.synchronize()
     if dist:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
     l0 = cs.launch_count()
+    t_timed0 = time.perf_counter()
     if ss.slab:
         ms = float(lib.custen_slab_time_run(ss.slab, args.steps))     # events on the slab's stream, synchronises
     else:
@@ -439,7 +441,7 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
     launches_timed = cs.launch_count() - l0
-    clocks = sampler.stop()
+    t_timed1 = time.perf_counter()
     if dist:
         dist.barrier()
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
@@ -500,6 +502,23 @@ def run_ours(args, rank, world, local_rank):
                         "the neighbour inside the kernel, in front of the halo rows only - no exchange step, no barrier "
                         "kernel; the NCCL figure is the same rows sent with send/recv on their own (latency-bound)"}
         del top, bot
+    # clocks and throttle reasons under this load.  K steps take 7 - 60 ms here, less than nvidia-smi's sampling period, so
+    # when the timed region was too short to be sampled reliably the same loop is repeated UNTIMED for half a second (after
+    # the parity check has read its rows) and sampled there; the same number of extra steps on every rank.
+    if ms >= 400.0:
+        clocks = sampler.stop(t_timed0, t_timed1)
+        clocks["window"] = "timed region"
+    else:
+        extra = int(min(20000, max(args.steps, 500.0 / (ms / args.steps))))
+        if dist:
+            dist.barrier()
+        t_rep0 = time.perf_counter()
+        ss.run(extra)
+        ss.synchronize()
+        t_rep1 = time.perf_counter()
+        clocks = sampler.stop(t_rep0 + 0.05, t_rep1)
+        clocks["window"] = ("untimed repeat of the timed loop (%d more steps, %.0f ms) right after it: the timed region, %.1f ms, "
+                            "is shorter than nvidia-smi's sampling period" % (extra, 1e3 * (t_rep1 - t_rep0), ms))
     ss.destroy()
     ms_per_step = ms / args.steps
     value = n * n / ms_per_step / 1e6  # Gpoints/s, whole job

@@ -172,9 +172,7 @@ def test_num_tiles_do_not_change_results(name, tiles):
         assert ol.count_diff(gu.run_ours(c, inp, kind=kind, tiles=tiles), want) == 0
 
 
-@pytest.mark.parametrize("name", ["x_p_5pt", "y_p_5pt", "xy_p_cross_tiles", "xy_p_fun_cubic", "xy_np_5x5"])
-def test_swap_time_stepping(name):
-    """Create -> (Compute, Swap) x 3, as a time stepper uses the API (Swap re-aliases in/out and the seams)."""
+def _time_step_three_times(name, kind, sync, offload=cs.DEVICE, tiles=None):
     c = next(x for x in cases.CASES if x["name"] == name)
     scale = 1.0 / max(1.0, float(np.sum(np.abs(c["coef"]))))
     coef = c["coef"] * scale  # keep the iteration bounded
@@ -185,13 +183,14 @@ def test_swap_time_stepping(name):
         a, b = b, a
     want_in, want_out = a, b  # after 3 swaps: `a` holds the newest field
 
-    buf = gu.Buffers("device", inp, np.full_like(inp, cases.SENTINEL), coef)
+    buf = gu.Buffers(kind, inp, np.full_like(inp, cases.SENTINEL), coef)
     st = cs.Stencil2D(c["variant"], c["nx"], c["ny"], buf.out, buf.inp, buf.coef, H=c["H"], L=c["L"], R=c["R"], V=c["V"],
-                      T=c["T"], B=c["B"], fun=c["fun"], numCoe=c["numCoe"], numTiles=c["tiles"], block=c["block"])
+                      T=c["T"], B=c["B"], fun=c["fun"], numCoe=c["numCoe"], numTiles=tiles or c["tiles"], block=c["block"])
     cur_in, cur_out = buf.inp, buf.out
     for _ in range(3):
-        st.compute(cs.DEVICE)
-        cs.device_synchronize()
+        st.compute(offload)
+        if sync:
+            cs.device_synchronize()
         st.swap(cur_out)  # the array that becomes the next input
         cur_in, cur_out = cur_out, cur_in
     # three swaps: the newest field sits in the array that started as `out`
@@ -201,6 +200,22 @@ def test_swap_time_stepping(name):
     buf.free()
     assert ol.count_diff(newest, want_in) == 0
     assert ol.count_diff(older, want_out) == 0
+
+
+@pytest.mark.parametrize("name", ["x_p_5pt", "y_p_5pt", "xy_p_cross_tiles", "xy_p_fun_cubic", "xy_np_5x5"])
+def test_swap_time_stepping(name):
+    """Create -> (Compute, Swap) x 3, as a time stepper uses the API (Swap re-aliases in/out and the seams)."""
+    _time_step_three_times(name, "device", sync=True)
+
+
+@pytest.mark.parametrize("kind,offload,tiles", [("device", cs.DEVICE, None), ("pinned", cs.HOST, 4), ("pageable", cs.HOST, 4),
+                                                ("managed", cs.DEVICE, 4), ("managed", cs.HOST, 4)])
+@pytest.mark.parametrize("name", ["y_p_5pt", "xy_p_cross_tiles", "xy_p_fun_cubic", "xy_np_5x5"])
+def test_compute_swap_compute_without_a_sync_in_between(name, kind, offload, tiles):
+    """Consecutive calls on one handle are ordered on the device: the next call's uploads must not overwrite a staging
+    slot a kernel still reads, nor read a host array the previous call's downloads still write (plan.cu, three-way join
+    on entry); unified memory goes pipeline -> resident / zero-copy along the way."""
+    _time_step_three_times(name, kind, sync=False, offload=offload, tiles=tiles)
 
 
 def test_shapes_the_tma_path_cannot_take_use_the_fallback():

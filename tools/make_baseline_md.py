@@ -12,20 +12,23 @@ def last_json(path):
 
 def main():
     ref = json.load(open(P("r1_reference_gpu_16384.json")))["rows"]
-    b = last_json(P("r1_bench_n1.json"))
+    b = last_json(P("r2_bench_n1.json"))
     tab = b["variants_16384"]
-    multi = {n: last_json(P(f"r1_bench_n{n}.json")) for n in (2, 4, 8) if os.path.exists(P(f"r1_bench_n{n}.json"))}
+    peak = b["roofline"]["peak"]
+    multi = {n: last_json(P(f"r2_bench_n{n}.json")) for n in (2, 4, 8) if os.path.exists(P(f"r2_bench_n{n}.json"))}
     L = []
-    L.append("""
-## 5. Measured on B200 (round 1)
+    L.append(f"""
+## 5. Measured on B200 (round 2)
 
-All numbers: B200 (148 SMs; SM clock sampled under load between 1575 and 1965 MHz, `sw_power_cap` reported on some boxes
-and kept in the bench line's `clocks`, no thermal or hardware slow-down), FP64, grids device-resident unless
-stated, CUDA-event timing (3 warm-ups, 10-20 timed sweeps, inputs far larger than L2). Roofline denominator: the driver's
-measured copy bandwidth 6548.5 GB/s (`MEASURED_PEAKS.json`); algorithmic traffic 16 B/point (WENO: 32). Raw lines:
-`profiles/r1_*.json`; regenerate this section with `python tools/make_baseline_md.py`. Every `gpurun` call lands on a
-different B200: over this round's runs the headline value (config 4, one GPU) came out at 362, 366, 371, 376, 378, 381
-and 406 Gpt/s (the power-capped boxes at both ends of that range); the table below is from the last run.
+All numbers: B200 (148 SMs; SM clock under load 1900-1965 MHz, `sw_power_cap` reported on most boxes and kept in the
+bench line's `clocks`, no thermal or hardware slow-down), FP64, grids device-resident unless stated, CUDA-event timing
+(3 warm-ups, 10-20 timed sweeps, inputs far larger than L2). Roofline denominator: the driver's measured copy bandwidth
+{peak:.0f} GB/s (`MEASURED_PEAKS.json`); algorithmic traffic 16 B/point (WENO: 32). Raw lines: `profiles/r2_bench_n*.json`;
+regenerate this section with `python tools/make_baseline_md.py`. Every `gpurun` call lands on a different B200 and the
+same kernel moves by a few per cent from box to box: the headline value (config 4, one GPU) came out at 372, 375, 388,
+393 and 395 Gpt/s over this round's runs; the tables below are from the last complete run at each GPU count (the
+single-GPU line predates the last change to the tile-family kernels, `profiles/r2_tile_carry_modes.log`, which added 4-5 %
+to XpFun / XnpFun and to XYpFun at 32768^2 on the box it was measured on).
 
 ### 5.1 Every variant on 16384^2 (target: >= 80 % of HBM peak) - new engine vs the reference's own kernels on the same GPU
 
@@ -41,15 +44,18 @@ and 406 Gpt/s (the power-capped boxes at both ends of that range); the table bel
             op = f"{t['opaque_pointer_gpoints_per_s']:.0f} Gpt/s"
             if r and r.get("gpoints_per_s"):
                 op += f" ({t['opaque_pointer_gpoints_per_s'] / r['gpoints_per_s']:.1f}x)"
+        if "random_fields_gpoints_per_s" in t:
+            op = f"random fields: {t['random_fields_gpoints_per_s']:.1f} Gpt/s"
         L.append(f"| {v} | {rg} | {t['gpoints_per_s']:.1f} Gpt/s = {t['hbm_gbs']:.0f} GB/s ({t['path']}) | {100 * t['frac_of_peak']:.1f} % | {sp} | {op} |")
     L.append(f"""
 Stencils: X/Y 9-point 8th-order second derivative (`examples/src/2d_x_p.cu:99-114`), XY weights 3x3 cross derivative
 (`2d_xy_p.cu:112-120`), XY Fun the Cahn-Hilliard `c^3 - c` function through a 3x3 Laplacian (`cuPentCahnADI.cu:164-188`),
-WENO5 advection with random velocities of both signs. The reference's Fun kernels need more than 64 registers on
+WENO5 advection on the fields of the reference's own program (`examples/src/2d_xyWENOADV_p.cu:97-101`) and on random
+fields (the reference kernel's figure is for random fields). The reference's Fun kernels need more than 64 registers on
 sm_100, so its examples' 32x32 blocks fail to launch ("too many resources"); 32x16 is used for them. `XYpFun` with the
 solver's 8x8 blocks: {ref['XYpFun_8x8']['gpoints_per_s']:.1f} Gpt/s. "stream_inline" = the user function is registered
 (`include/cuSten_fun.h`) and inlined; the last column is the same call through the opaque device pointer (an
-unregistered user function).
+unregistered user function; DESIGN.md 3.1 on why that road is callee-bound).
 
 ### 5.2 BASELINE.json configs
 
@@ -58,55 +64,66 @@ unregistered user function).
     c1 = b.get("config1_serial_cpu_cahn_512", {})
     L.append(f"| 1: serial CPU Cahn-Hilliard, 512^2, T = 10 (1019 steps), 1 host core of the GPU box ({c1.get('host_threads_available')} threads available) | {c1.get('seconds', float('nan')):.2f} s = {c1.get('mpoint_steps_per_s')} Mpoint-steps/s |")
     L.append(f"| 2: 2d_x_p 9-pt, 8192^2, 1 GPU | {b['x_p_8192']['gpoints_per_s']:.1f} Gpt/s = {100 * b['x_p_8192']['frac_of_peak']:.1f} % of HBM peak (bit-identical to the reference kernel at this size, `tests/test_parity_gpu.py::test_reference_kernels_at_config2_size`) |")
-    L.append(f"| 3: 2d_xy_np 3x3, 16384^2, numTiles = 4, device-resident | {b['xy_np_16384_t4']['gpoints_per_s']:.1f} Gpt/s = {100 * b['xy_np_16384_t4']['frac_of_peak']:.1f} % of HBM peak (tiles are contiguous: one launch) |")
-    L.append(f"| 4: 2d_xy_p_fun (c^3 - c), 32768^2, 1 GPU | {b['value']:.1f} Gpt/s = {b['roofline']['achieved']:.0f} GB/s = {100 * b['roofline']['frac']:.1f} % of HBM peak; ncu DRAM traffic {b['roofline']['traffic'] / 1e9:.2f} GB per sweep vs 17.18 GB algorithmic |")
+    L.append(f"| 3: 2d_xy_np 3x3, 16384^2, numTiles = 4, device-resident | {b['xy_np_16384_t4']['gpoints_per_s']:.1f} Gpt/s = {100 * b['xy_np_16384_t4']['frac_of_peak']:.1f} % of HBM peak (tiles are contiguous: one launch; bit-identical to the reference kernel at this size) |")
     um = b.get("xy_np_16384_t4_unified_memory") or {}
     if "default" in um:
         d0, r0 = um["default"], um["reference_pipeline"]
         L.append(f"| 3: same sweep on unified memory (`cudaMallocManaged`, what the reference requires), numTiles = 4, offload = DEVICE | "
-                 f"{d0['offload_DEVICE']['gpoints_per_s']:.0f} Gpt/s ({d0['offload_DEVICE']['ms_per_step']:.2f} ms; the grid is already on the GPU, "
-                 f"no prefetch is issued); the reference's prefetch pipeline on every call: {r0['offload_DEVICE']['gpoints_per_s']:.0f} Gpt/s "
-                 f"({r0['offload_DEVICE']['ms_per_step']:.2f} ms, the no-op prefetches cost more than the sweep) |")
+                 f"**{d0['offload_DEVICE']['gpoints_per_s']:.0f} Gpt/s** ({d0['offload_DEVICE']['ms_per_step']:.2f} ms; the grid is already on the GPU, "
+                 f"no prefetch is issued; round 1: 273); the reference's prefetch pipeline on every call: {r0['offload_DEVICE']['gpoints_per_s']:.0f} Gpt/s "
+                 f"({r0['offload_DEVICE']['ms_per_step']:.2f} ms, the no-op prefetches cost more than the sweep). CPU- or GPU-first-touched pages make no difference: `profiles/r2_um_probe.log` |")
         L.append(f"| 3: same, offload = HOST (the grid lives on the CPU between sweeps) | "
                  f"{d0['offload_HOST']['gpoints_per_s']:.2f} Gpt/s ({d0['offload_HOST']['ms_per_step']:.0f} ms; swept in place over the host link, "
                  f"{d0['offload_HOST']['host_link_gbs_each_way']} GB/s each way: 8 B in + 8 B out per point); the reference's pipeline "
                  f"(every tile migrated to the GPU and back, 16 B per point each way): {r0['offload_HOST']['gpoints_per_s']:.2f} Gpt/s "
                  f"({r0['offload_HOST']['ms_per_step']:.0f} ms, {r0['offload_HOST']['host_link_gbs_each_way']} GB/s each way) |")
+    L.append(f"| 4: 2d_xy_p_fun (c^3 - c), 32768^2, time-stepped (Compute + Swap per step), 1 GPU | {b['value']:.1f} Gpt/s = {b['roofline']['achieved']:.0f} GB/s = {100 * b['roofline']['frac']:.1f} % of HBM peak; seam-row parity against the oracle: {b['parity']['bits_differing']} differing bits; ncu DRAM traffic {b['roofline']['traffic'] / 1e9:.2f} GB per sweep vs 17.18 GB algorithmic (stored figure) |")
     for n, d in sorted(multi.items()):
         he = d.get("halo_exchange") or {}
-        L.append(f"| 4: same grid on {n} GPUs (y-slabs, strong scaling, {d['config']['parallelism']}) | {d['value']:.0f} Gpt/s, {d['ms_per_step']:.3f} ms/sweep = {100 * d['value'] / (n * b['value']):.0f} % of ideal"
-                 + (f"; halo rows {he['bytes_received_per_gpu_per_sweep'] // 1024} KiB/GPU/sweep read over NVLink inside the sweep; the same rows as an NCCL send/recv exchange take {he['nccl_exchange_us']} us ({he['nccl_exchange_nvlink_gbs_per_gpu']} GB/s per GPU, latency-bound)" if he else "") + " |")
+        L.append(f"| 4: same grid on {n} GPUs ({d['config']['parallelism']}, strong scaling) | **{d['value']:.0f} Gpt/s**, {d['ms_per_step']:.3f} ms/step, {100 * d['roofline']['frac']:.1f} % of HBM peak per GPU, {d['value'] / b['value']:.2f}x the single-GPU line above; parity: {d['parity']['rows_checked']} seam rows, {d['parity']['bits_differing']} differing bits, {d['parity']['neighbour_wait_timeouts']} wait time-outs"
+                 + (f"; halo rows {he['bytes_received_per_gpu_per_sweep'] // 1024} KiB/GPU/sweep read over NVLink inside the sweep (the same rows as an NCCL send/recv exchange on their own: {he['nccl_exchange_us']} us)" if he else "") + " |")
     e = b["e2e"]
-    L.append(f"| 4: end to end from pinned HOST buffers (numTiles = {e['numTiles']} staged pipeline, H2D + D2H inside the timed region), 1 GPU | {e['value']:.2f} Gpt/s (PCIe-bound: 2 x 8 GiB per sweep in {e['ms_per_step']:.0f} ms) |")
+    L.append(f"| 4: end to end from pinned HOST buffers (numTiles = {e['numTiles']} staged pipeline, H2D + D2H inside the timed region), 1 GPU | {e['value']:.2f} Gpt/s = {e['host_link_gbs']} GB/s over the host link; plain `cudaMemcpyAsync` both ways at once on the same buffers: {e['host_link_ceiling_gbs']} GB/s (`link_frac` {e['link_frac']}) |")
+    for n, d in sorted(multi.items()):
+        e2 = d.get("e2e")
+        if e2:
+            L.append(f"| 4: end to end, {n} GPUs | {e2['value']:.2f} Gpt/s = {e2['host_link_gbs']} GB/s aggregate; all ranks' plain copies at once: {e2['host_link_ceiling_gbs']} GB/s (`link_frac` {e2['link_frac']}): the box's host memory system is the wall |")
     cb = b.get("cpu_baseline") or {}
     if cb.get("value"):
         L.append(f"| CPU baseline for the headline path: the reference's serial `nonlinearRHS`, 1 core | {cb['value'] * 1e3:.1f} Mpoints/s ({cb['sample']}) |")
     ch = {k: b[k] for k in b if k.startswith("cahn_hilliard_")}
     L.append("""
-### 5.3 Config 5: Cahn-Hilliard ADI (bit-identical to the reference's GPU solver)
+### 5.3 Config 5: Cahn-Hilliard ADI
 
-| n | reference GPU solver (sm_100 rebuild, managed memory, 13 syncs/step) | new engine, 1 GPU (fused right-hand side + TMA-fed solve) | speed-up | same step through the engine's public API (cuStenCompute2D*, cp.async solve) | reference serial CPU (1 core) |
-|---|---|---|---|---|---|""")
+| n | reference GPU solver (sm_100 rebuild, managed memory, 13 syncs/step) | new engine, 1 GPU, default (row-streaming right-hand side + partitioned solves; within 1e-13 of the reference per step) | speed-up | bit-identical road (fused right-hand side + TMA-fed solve in the reference's operation order) | same step through the engine's public API (cuStenCompute2D*, cp.async solve) | reference serial CPU (1 core) |
+|---|---|---|---|---|---|---|""")
     for n in (512, 4096):
         r = ref.get(f"cahn_hilliard_{n}")
         o = ch.get(f"cahn_hilliard_{n}")
         if r and o:
             cpu = f"{c1['seconds'] / c1['steps'] * 1e3:.1f} ms/step" if n == 512 and c1.get("seconds") else "-"
             eng = f"{o['engine_path_ms_per_step']:.3f} ms/step" if "engine_path_ms_per_step" in o else "-"
-            L.append(f"| {n} | {r['ms_per_step']:.3f} ms/step | {o['ms_per_step']:.3f} ms/step ({o['mpoint_steps_per_s'] / 1e3:.2f} Gpoint-steps/s) | {r['ms_per_step'] / o['ms_per_step']:.0f}x | {eng} | {cpu} |")
-    if os.path.exists(P("r1_cahn_slab_multi_gpu.jsonl")):
-        L.append("\nMulti-GPU (y-slabs, peer halos, two all-to-all transposes per step; bit-identical to 1 GPU):\n\n| n | GPUs | ms/step | |\n|---|---|---|---|")
-        for ln in open(P("r1_cahn_slab_multi_gpu.jsonl")):
-            d = json.loads(ln)
-            L.append(f"| {d['n']} | {d['gpus']} | {d['ms_per_step']:.3f} | {d.get('note', '')} |")
-        L.append("\nThe bit-identical solve is a sequential recurrence per system (~0.15 ms at n = 4096 however few systems a GPU "
-                 "holds), so config 5 gains little from more GPUs; see DESIGN.md section 7.")
+            bit = f"{o['bit_identical_ms_per_step']:.3f} ms/step" if "bit_identical_ms_per_step" in o else "-"
+            L.append(f"| {n} | {r['ms_per_step']:.3f} ms/step | **{o['ms_per_step']:.3f} ms/step** ({o['mpoint_steps_per_s'] / 1e3:.2f} Gpoint-steps/s; vs the bit-identical road after {o['parity']['steps_compared']} steps: {o['parity']['rel_vs_bit_identical_road']:.1e}) | {r['ms_per_step'] / o['ms_per_step']:.0f}x | {bit} | {eng} | {cpu} |")
+    rows = [(1, ch["cahn_hilliard_4096"]["ms_per_step"], "")]
+    for n, d in sorted(multi.items()):
+        c = d.get("cahn_hilliard_4096")
+        if c and "ms_per_step" in c:
+            rows.append((n, c["ms_per_step"], f"bits differing from the single-GPU solver after {c['parity']['steps_compared']} steps: {c['parity']['bits_differing_vs_single_gpu']}; wait time-outs: {c['parity']['neighbour_wait_timeouts']}"))
+    L.append("\nMulti-GPU, 4096^2 (y-slabs; per step a GPU reads from its neighbours only 2 + 2 halo rows of c and c(t - dt) and 4 interface "
+             "values per system of the y-partitions within reach of the seam - no all-to-all; `bench.py --gpus N`):\n\n| GPUs | ms/step | speed-up | |\n|---|---|---|---|")
+    for n, ms, note in rows:
+        L.append(f"| {n} | {ms:.3f} | {rows[0][1] / ms:.2f}x | {note} |")
     L.append("""
-Step breakdown at 4096^2 on 1 GPU (ncu launch list, `profiles/r1_launch_list_cahn4096.md`): right-hand side in one pass
-117 us (shared-memory bandwidth and FP64 bound; it reads c and cOld once, 269 MB, and writes rhs^T), two cyclic pentadiagonal
-solves 2 x 144 us (dependent-FP64-latency bound: 6 chained operations of 8 cycles per row and system, `profiles/r1_fp64_latency.log`,
-i.e. 103 us at best), rank-2 correction + transpose 55 us, correction + `findNew` 79 us (4 array passes, at the HBM roofline).
-The same step at the start of the round (separate cBar / stencil / rhs passes, cp.async solve): 0.92 ms.
+Round 1 for comparison: 0.541 ms/step on one GPU (bit-identical road only), 0.84 ms on two and 0.72 ms on eight (two
+all-to-all transposes per step around a recurrence that costs the same however few systems a GPU holds).
+
+Step breakdown at 4096^2 on 1 GPU (ncu launch list, `profiles/r2_launches_cahn4096.csv`; 88 B/point/step = 1.476 GB, 226 us at the
+measured HBM peak): row-streaming right-hand side 82 us (24 B/pt), x-direction partition-local solves 51 us (16 B/pt),
+y-direction partition-local solves with the x-correction applied on load 57 us (16 B/pt), the two interface reductions
+2 x 9 us, y-correction + `findNew` 88 us (32 B/pt): 0.294 ms = 77 % of the roofline. The reference's unmodified driver
+linked against the new `libcuSten.a` (only its two stencil sweeps change): 1.28 -> 0.74 ms/step at 512^2, 14.3 -> 13.1 at
+4096^2, same bits (`profiles/r2_dropin_config5.log`).
 """)
     s = open(os.path.join(ROOT, "BASELINE.md")).read()
     if "\n## 5. Measured on B200" in s:
