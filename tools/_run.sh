@@ -1,18 +1,12 @@
 mkdir -p gpurun_out
-nvidia-smi -L | wc -l
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 8 --steps 20 --warmup 3 > gpurun_out/r2r_bench_n8.json 2> gpurun_out/r2r_bench_n8.err; echo "bench rc=$?"
-tail -c 400 gpurun_out/r2r_bench_n8.err
+timeout 1500 python -m pytest tests -q -m gpu -x --durations=5 > gpurun_out/r2s_tests.log 2>&1; echo "rc=$?" >> gpurun_out/r2s_tests.log
+grep -n "^E   \|passed\|failed\|^FAILED\|rc=" gpurun_out/r2s_tests.log | cut -c1-250 | head -20
+timeout 900 python bench.py > gpurun_out/r2s_bench_n1.json 2> gpurun_out/r2s_bench_n1.err; echo "bench rc=$?"
+tail -c 300 gpurun_out/r2s_bench_n1.err
 python - <<'P'
 import json
-d=json.loads(open('gpurun_out/r2r_bench_n8.json').read().strip().splitlines()[-1])
-print(d['value'], d['ms_per_step'], d['roofline']['frac'], d['e2e']['value'], d['e2e']['link_frac'], d['parity'])
-print(d.get('cahn_hilliard_4096'))
-print(d.get('halo_exchange'))
+d=json.loads(open('gpurun_out/r2s_bench_n1.json').read().strip().splitlines()[-1])
+print(d['value'], d['ms_per_step'], d['roofline']['frac'], d['e2e']['value'], d['clocks'])
+print({k:(v['gpoints_per_s'], v.get('opaque_pointer_gpoints_per_s'), v.get('random_fields_gpoints_per_s')) for k,v in d['variants_16384'].items()})
 P
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29534 bench.py --gpus 4 --steps 20 --warmup 3 --no-e2e > gpurun_out/r2r_bench_n4.json 2> gpurun_out/r2r_bench_n4.err; echo "bench4 rc=$?"
-python - <<'P'
-import json
-d=json.loads(open('gpurun_out/r2r_bench_n4.json').read().strip().splitlines()[-1])
-print(d['value'], d['ms_per_step'], d['roofline']['frac'], d['parity'])
-print(d.get('cahn_hilliard_4096'))
-P
+timeout 120 python bench.py --impl reference --steps 3 --warmup 1 | cut -c1-400
