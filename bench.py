@@ -772,7 +772,7 @@ def run_ours(args, rank, world, local_rank):
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get(args.workload if world == 1 else "", None)
-        traffic_src = "stored_from_profiles (ncu --set full capture of this kernel, profiles/r1_ncu_full_summary.md); not measured in this run"
+        traffic_src = "stored_from_profiles (ncu --set full capture of this kernel, profiles/r2_ncu_full_summary.md); not measured in this run"
     achieved = value / world * ALG_BYTES_PER_POINT  # GB/s per GPU
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

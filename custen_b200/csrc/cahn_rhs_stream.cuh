@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(RS_NT, 2) k_rhs_stream(const double* __restric
         for (int s = 0; s < RS_NS; ++s)
         {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(rs::saddr(bars + s)) : "memory");
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rs::saddr(bars + RS_NS + s)), "r"(RS_NT / 32) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rs::saddr(bars + RS_NS + s)), "r"(RS_NT) : "memory");
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -205,8 +205,10 @@ __global__ void __launch_bounds__(RS_NT, 2) k_rhs_stream(const double* __restric
         }
         if (kk % RS_SR == RS_SR - 1)
         {
-            __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(rs::saddr(bars + RS_NS + slot)) : "memory");
+            // every thread hands the stage back itself (compute-sanitizer's racecheck follows a thread's own arrival, not
+            // "__syncwarp, then lane 0 arrives for the warp": with that form it reports the refill as racing with the other
+            // lanes' reads)
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(rs::saddr(bars + RS_NS + slot)) : "memory");
         }
     }
 }

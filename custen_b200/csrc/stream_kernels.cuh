@@ -300,8 +300,8 @@ __device__ __forceinline__ void producer_loop(const StreamArgs& a, unsigned char
             }
             if (a.warp_carry)
             {
-                // The stage's barrier takes two arrivals in this mode: the one above (with the byte count of the bulk
-                // copies) and this one, after the carry rows are in place.  The previous stage (always a full one) must
+                // The stage's barrier takes 33 arrivals in this mode: the one above (with the byte count of the bulk
+                // copies) and one per lane, after the carry rows are in place.  The previous stage (always a full one) must
                 // have landed before its last PFX rows are read; its slot cannot be refilled under the copy, the
                 // refill being issued by this same warp later.
                 if (carry)
@@ -315,7 +315,7 @@ __device__ __forceinline__ void producer_loop(const StreamArgs& a, unsigned char
                     for (int e = lane; e < n2; e += 32) dst2[e] = src[e];
                     __syncwarp();
                 }
-                if (lane == 0) mbar_arrive(bar);
+                mbar_arrive(bar);   // every lane, for the rows it copied
             }
             if (++s == NS) { s = 0; ph ^= 1; }
         }
@@ -583,7 +583,7 @@ template <int NT, int SR, int NS, int MINB, class Op>
 __global__ void __launch_bounds__(NT + 32, MINB) stream_tile_kernel(const __grid_constant__ StreamArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    stream_prologue<NS>(smem, a.warp_carry ? NT / 32 : 1, a.warp_carry ? 2 : 1);
+    stream_prologue<NS>(smem, a.warp_carry ? NT : 1, a.warp_carry ? 33 : 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == NT / 32)
@@ -670,9 +670,11 @@ __global__ void __launch_bounds__(NT + 32, MINB) stream_tile_kernel(const __grid
 
         if (a.warp_carry)
         {
-            // the producer warp moves the carry rows: every consumer warp hands the stage back on its own
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty0 + 8 * s);
+            // the producer warp moves the carry rows: every consumer thread hands the stage back on its own (one arrival
+            // per thread rather than "__syncwarp, lane 0 arrives": same speed, and compute-sanitizer's racecheck only
+            // follows a thread's own arrival - with the per-warp form it reports the refill as racing with the other
+            // lanes' reads, profiles/r2_compute_sanitizer.md)
+            mbar_arrive(empty0 + 8 * s);
         }
         else
         {
@@ -701,6 +703,9 @@ struct TileBig { static constexpr int NT = 512, SR = 16, NS = 3, MAXCPS = 1; };
 // WENO is compute-bound (18 single-precision powf per point): as many warps as the register file allows
 // (480 / 608-thread CTAs and two or three smaller CTAs per SM measured within 3 % or slower: profiles/r2_weno_geom_v2.log).
 struct TileWeno { static constexpr int NT = 736, SR = 8, NS = 2, MAXCPS = 1; };
+struct TileWeno1 { static constexpr int NT = 608, SR = 8, NS = 3, MAXCPS = 1; };
+struct TileWeno2 { static constexpr int NT = 736, SR = 4, NS = 3, MAXCPS = 1; };
+struct TileWeno3 { static constexpr int NT = 672, SR = 6, NS = 3, MAXCPS = 1; };
 
 struct LaunchGeom
 {

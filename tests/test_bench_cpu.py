@@ -48,3 +48,24 @@ def test_time_stepping_workload_stays_bounded():
     okw = {k: v for k, v in kw.items() if k != "fun"}
     final, _ = ol.oracle_time_steps("XYpFun", f, np.zeros_like(f), coef, 23, fun="cubic_xy", **okw)
     assert 1e-3 < np.abs(final).max() < 0.2
+
+
+def test_clock_sampler_summarises_only_the_samples_of_the_requested_window():
+    class FakeProc:
+        def terminate(self):
+            pass
+
+    class FakeThread:
+        def join(self, timeout=None):
+            pass
+
+    s = bench.ClockSampler.__new__(bench.ClockSampler)
+    s.proc, s.th = FakeProc(), FakeThread()
+    idle = ["210", "1965", "140.0", "Not Active", "Not Active", "Not Active", "Not Active"]
+    load = ["1905", "1965", "950.0", "Not Active", "Not Active", "Not Active", "Active"]
+    s.rows = [(0.10, idle), (0.20, idle), (1.00, load), (1.05, load), (1.10, ["1935"] + load[1:]), (2.0, idle)]
+    got = s.stop(0.95, 1.2)
+    assert got["samples"] == 3 and got["sm_mhz"] == 1905.0 and got["sm_max_mhz"] == 1965.0
+    assert got["reasons"] == ["sw_power_cap"]
+    s.rows = s.rows[:2]
+    assert s.stop(0.95, 1.2) == {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}

@@ -1,12 +1,14 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -q -m gpu -x --durations=5 > gpurun_out/r2s_tests.log 2>&1; echo "rc=$?" >> gpurun_out/r2s_tests.log
-grep -n "^E   \|passed\|failed\|^FAILED\|rc=" gpurun_out/r2s_tests.log | cut -c1-250 | head -20
-timeout 900 python bench.py > gpurun_out/r2s_bench_n1.json 2> gpurun_out/r2s_bench_n1.err; echo "bench rc=$?"
-tail -c 300 gpurun_out/r2s_bench_n1.err
-python - <<'P'
-import json
-d=json.loads(open('gpurun_out/r2s_bench_n1.json').read().strip().splitlines()[-1])
-print(d['value'], d['ms_per_step'], d['roofline']['frac'], d['e2e']['value'], d['clocks'])
-print({k:(v['gpoints_per_s'], v.get('opaque_pointer_gpoints_per_s'), v.get('random_fields_gpoints_per_s')) for k,v in d['variants_16384'].items()})
-P
-timeout 120 python bench.py --impl reference --steps 3 --warmup 1 | cut -c1-400
+timeout 1200 python -m pytest tests/test_parity_gpu.py tests/test_weno_gpu.py tests/test_slab_c_gpu.py tests/test_cahn_gpu.py tests/test_cahn_slab_gpu.py -q -m gpu -x 2>&1 | tail -3
+filt() { grep -v "Host Frame" | grep "Error: \|SUMMARY\|passed\|failed\|smoke ok\|ms/step" | cut -c1-200 | head -8; }
+{
+for tool in memcheck racecheck; do
+  echo "## $tool: python __graft_entry__.py --smoke"; timeout 420 compute-sanitizer --tool $tool --print-limit 4 python __graft_entry__.py --smoke 2>&1 | filt
+  echo "## $tool: python tools/cahn_steps.py 256 3"; timeout 420 compute-sanitizer --tool $tool --print-limit 4 python tools/cahn_steps.py 256 3 2>&1 | filt
+  for t in "tests/test_weno_gpu.py -k windows" "tests/test_slab_c_gpu.py -k static_input" "tests/test_cahn_slab_gpu.py -k 256-2-64-7" "tests/test_parity_gpu.py -k opaque_function_pointer_road"; do
+    echo "## $tool: pytest $t"
+    timeout 420 compute-sanitizer --tool $tool --print-limit 4 python -m pytest $t -q -m gpu -x 2>&1 | filt
+  done
+done
+} > gpurun_out/r2w_sanitizer.log 2>&1
+cat gpurun_out/r2w_sanitizer.log
