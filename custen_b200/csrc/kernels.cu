@@ -343,14 +343,7 @@ int launch_band(const Band& b, cudaStream_t st)
 
     if (b.weno)
     {
-        static const int geom = getenv("CUSTEN_WENO_GEOM") ? atoi(getenv("CUSTEN_WENO_GEOM")) : 0;
-        switch (geom)
-        {
-        case 1: launch_tile_geom<TileWeno1, 1, OpWeno>(a, st); break;
-        case 2: launch_tile_geom<TileWeno2, 1, OpWeno>(a, st); break;
-        case 3: launch_tile_geom<TileWeno3, 1, OpWeno>(a, st); break;
-        default: launch_tile_geom<TileWeno, 1, OpWeno>(a, st);
-        }
+        launch_tile_geom<TileWeno, 1, OpWeno>(a, st);
         return PATH_STREAM_TILE;
     }
     const bool lodd = (b.L & 1) != 0;

@@ -701,11 +701,9 @@ __global__ void __launch_bounds__(NT + 32, MINB) stream_tile_kernel(const __grid
 struct TileSmall { static constexpr int NT = 256, SR = 8, NS = 3, MAXCPS = 2; };
 struct TileBig { static constexpr int NT = 512, SR = 16, NS = 3, MAXCPS = 1; };
 // WENO is compute-bound (18 single-precision powf per point): as many warps as the register file allows
-// (480 / 608-thread CTAs and two or three smaller CTAs per SM measured within 3 % or slower: profiles/r2_weno_geom_v2.log).
+// (480 / 608-thread CTAs, two or three smaller CTAs per SM and three-stage rings of 608 x 8, 736 x 4 and 672 x 6 rows
+// measured within 3 % or slower: profiles/r2_weno_geom_v2.log, r2_weno_geom_v3.log).
 struct TileWeno { static constexpr int NT = 736, SR = 8, NS = 2, MAXCPS = 1; };
-struct TileWeno1 { static constexpr int NT = 608, SR = 8, NS = 3, MAXCPS = 1; };
-struct TileWeno2 { static constexpr int NT = 736, SR = 4, NS = 3, MAXCPS = 1; };
-struct TileWeno3 { static constexpr int NT = 672, SR = 6, NS = 3, MAXCPS = 1; };
 
 struct LaunchGeom
 {

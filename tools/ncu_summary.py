@@ -34,22 +34,25 @@ def main(out, reps):
     for rep in reps:
         raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(raw)))
-        hdr, units, vals = rows[0], rows[1], rows[2]
+        hdr, units = rows[0], rows[1]
         col = {h: i for i, h in enumerate(hdr)}
-        name = vals[col["Kernel Name"]]
-        lines.append(f"\n## {rep.split('/')[-1]}\n\n`{name}`\n\n| metric | value |\n|---|---|")
-        for k, label in KEYS:
-            if k in col:
-                lines.append(f"| {label} (`{k}`) | {vals[col[k]]} {units[col[k]]} |")
-        try:
-            rd = float(vals[col["dram__bytes_read.sum"]].replace(",", ""))
-            wr = float(vals[col["dram__bytes_write.sum"]].replace(",", ""))
-            u = units[col["dram__bytes_read.sum"]]
-            scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[u]
-            traffic[rep.split("/")[-1]] = (rd + wr) * scale
-            lines.append(f"| **DRAM traffic per launch** | {(rd + wr) * scale / 1e9:.3f} GB |")
-        except Exception:
-            pass
+        for k_idx, vals in enumerate(r for r in rows[2:] if len(r) == len(hdr)):
+            name = vals[col["Kernel Name"]]
+            tag = rep.split('/')[-1] + (f" (launch {k_idx + 1})" if k_idx else "")
+            lines.append(f"\n## {tag}\n\n`{name}`\n\n| metric | value |\n|---|---|")
+            for k, label in KEYS:
+                if k in col:
+                    lines.append(f"| {label} (`{k}`) | {vals[col[k]]} {units[col[k]]} |")
+            try:
+                rd = float(vals[col["dram__bytes_read.sum"]].replace(",", ""))
+                wr = float(vals[col["dram__bytes_write.sum"]].replace(",", ""))
+                scale_r = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[units[col["dram__bytes_read.sum"]]]
+                scale_w = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[units[col["dram__bytes_write.sum"]]]
+                if k_idx == 0:
+                    traffic[rep.split("/")[-1]] = rd * scale_r + wr * scale_w
+                lines.append(f"| **DRAM traffic per launch** | {(rd * scale_r + wr * scale_w) / 1e9:.3f} GB |")
+            except Exception:
+                pass
     open(out, "w").write("\n".join(lines) + "\n")
     print(traffic)
 
