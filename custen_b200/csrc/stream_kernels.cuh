@@ -700,10 +700,13 @@ __global__ void __launch_bounds__(NT + 32, MINB) stream_tile_kernel(const __grid
 // windows, 256-column strips and two CTAs per SM otherwise.
 struct TileSmall { static constexpr int NT = 256, SR = 8, NS = 3, MAXCPS = 2; };
 struct TileBig { static constexpr int NT = 512, SR = 16, NS = 3, MAXCPS = 1; };
-// WENO is compute-bound (18 single-precision powf per point): as many warps as the register file allows
-// (480 / 608-thread CTAs, two or three smaller CTAs per SM and three-stage rings of 608 x 8, 736 x 4 and 672 x 6 rows
-// measured within 3 % or slower: profiles/r2_weno_geom_v2.log, r2_weno_geom_v3.log).
-struct TileWeno { static constexpr int NT = 736, SR = 8, NS = 2, MAXCPS = 1; };
+// WENO is compute-bound (18 single-precision powf per point): as many warps as the register file allows, and a
+// consumer-warp count that is a multiple of four - 24 warps + the producer warp.  With 23 (736 threads) one scheduler
+// had five consumer warps, ran ahead and waited a tenth of the time on the next stage's barrier (ncu source view):
+// 736 -> 768 threads is +2.4 % on the reference example's fields and +5.6 % on random fields.  480 / 608-thread CTAs,
+// two or three smaller CTAs per SM and three-stage rings measured within 3 % or slower
+// (profiles/r2_weno_geom_v2.log, _v3.log, _v4.log).
+struct TileWeno { static constexpr int NT = 768, SR = 8, NS = 2, MAXCPS = 1; };
 
 struct LaunchGeom
 {
