@@ -44,14 +44,16 @@ to XpFun / XnpFun and to XYpFun at 32768^2 on the box it was measured on).
             op = f"{t['opaque_pointer_gpoints_per_s']:.0f} Gpt/s"
             if r and r.get("gpoints_per_s"):
                 op += f" ({t['opaque_pointer_gpoints_per_s'] / r['gpoints_per_s']:.1f}x)"
+        if "example_fields_gpoints_per_s" in t:
+            op = f"reference example's fields: {t['example_fields_gpoints_per_s']:.1f} Gpt/s"
         if "random_fields_gpoints_per_s" in t:
             op = f"random fields: {t['random_fields_gpoints_per_s']:.1f} Gpt/s"
         L.append(f"| {v} | {rg} | {t['gpoints_per_s']:.1f} Gpt/s = {t['hbm_gbs']:.0f} GB/s ({t['path']}) | {100 * t['frac_of_peak']:.1f} % | {sp} | {op} |")
     L.append(f"""
 Stencils: X/Y 9-point 8th-order second derivative (`examples/src/2d_x_p.cu:99-114`), XY weights 3x3 cross derivative
 (`2d_xy_p.cu:112-120`), XY Fun the Cahn-Hilliard `c^3 - c` function through a 3x3 Laplacian (`cuPentCahnADI.cu:164-188`),
-WENO5 advection on the fields of the reference's own program (`examples/src/2d_xyWENOADV_p.cu:97-101`) and on random
-fields (the reference kernel's figure is for random fields). The reference's Fun kernels need more than 64 registers on
+WENO5 advection on random fields (like the reference kernel's figure and round 1) and on the fields of the reference's
+own program (`examples/src/2d_xyWENOADV_p.cu:97-101`). The reference's Fun kernels need more than 64 registers on
 sm_100, so its examples' 32x32 blocks fail to launch ("too many resources"); 32x16 is used for them. `XYpFun` with the
 solver's 8x8 blocks: {ref['XYpFun_8x8']['gpoints_per_s']:.1f} Gpt/s. "stream_inline" = the user function is registered
 (`include/cuSten_fun.h`) and inlined; the last column is the same call through the opaque device pointer (an
