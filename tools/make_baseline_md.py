@@ -84,6 +84,11 @@ unregistered user function; DESIGN.md 3.1 on why that road is callee-bound).
         he = d.get("halo_exchange") or {}
         L.append(f"| 4: same grid on {n} GPUs ({d['config']['parallelism']}, strong scaling) | **{d['value']:.0f} Gpt/s**, {d['ms_per_step']:.3f} ms/step, {100 * d['roofline']['frac']:.1f} % of HBM peak per GPU, {d['value'] / b['value']:.2f}x the single-GPU line above; parity: {d['parity']['rows_checked']} seam rows, {d['parity']['bits_differing']} differing bits, {d['parity']['neighbour_wait_timeouts']} wait time-outs"
                  + (f"; halo rows {he['bytes_received_per_gpu_per_sweep'] // 1024} KiB/GPU/sweep read over NVLink inside the sweep (the same rows as an NCCL send/recv exchange on their own: {he['nccl_exchange_us']} us)" if he else "") + " |")
+    late = {n: last_json(P(f"r2_bench_n{n}_late.json")) for n in (2, 4) if os.path.exists(P(f"r2_bench_n{n}_late.json"))}
+    if late:
+        L.append("| 4: the same on a later box, final stencil kernels, `--no-e2e` | " + ", ".join(
+            f"{n} GPUs: {d['value']:.0f} Gpt/s = {100 * d['roofline']['frac']:.1f} % of HBM peak per GPU (SM clock under load {d['clocks']['sm_mhz']:.0f} MHz, {', '.join(d['clocks']['reasons']) or 'no throttle reason'})"
+            for n, d in sorted(late.items())) + " |")
     e = b["e2e"]
     L.append(f"| 4: end to end from pinned HOST buffers (numTiles = {e['numTiles']} staged pipeline, H2D + D2H inside the timed region), 1 GPU | {e['value']:.2f} Gpt/s = {e['host_link_gbs']} GB/s over the host link; plain `cudaMemcpyAsync` both ways at once on the same buffers: {e['host_link_ceiling_gbs']} GB/s (`link_frac` {e['link_frac']}) |")
     for n, d in sorted(multi.items()):
