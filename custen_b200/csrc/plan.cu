@@ -187,7 +187,8 @@ static void release_staging(Plan* p)
     {
         if (p->d_in[s]) cudaFree(p->d_in[s]);
         if (p->d_out[s]) cudaFree(p->d_out[s]);
-        p->d_in[s] = p->d_out[s] = nullptr;
+        if (p->d_aux[s]) cudaFree(p->d_aux[s]);
+        p->d_in[s] = p->d_out[s] = p->d_aux[s] = nullptr;
         if (p->events_ready)
         {
             cudaEventDestroy(p->ev_loaded[s]);
@@ -641,6 +642,7 @@ static void compute_staged(cuSten_t* h, Plan* p, const double* coef)
         {
             cudaMalloc(&p->d_in[k], need_rows * nx * sizeof(double));
             cudaMalloc(&p->d_out[k], (size_t)h->nyTile * nx * sizeof(double));
+            if (s.weno) cudaMalloc(&p->d_aux[k], (size_t)2 * h->nyTile * nx * sizeof(double));
             check("Allocating staging slot", dev);
         }
         p->stage_rows = need_rows;
@@ -675,6 +677,15 @@ static void compute_staged(cuSten_t* h, Plan* p, const double* coef)
         if (b.have_bottom)
             cudaMemcpyAsync(din + ((size_t)T + h->nyTile) * nx, b.bottom, (size_t)B * row_bytes, cudaMemcpyDefault,
                             s_load);
+        if (s.weno)
+        {
+            // the velocities of the tile's own rows (the kernel reads them per output point: no halo)
+            double* daux = p->d_aux[k];
+            cudaMemcpyAsync(daux, b.aux0, (size_t)h->nyTile * row_bytes, cudaMemcpyDefault, s_load);
+            cudaMemcpyAsync(daux + (size_t)h->nyTile * nx, b.aux1, (size_t)h->nyTile * row_bytes, cudaMemcpyDefault, s_load);
+            b.aux0 = daux;
+            b.aux1 = daux + (size_t)h->nyTile * nx;
+        }
         cudaEventRecord(p->ev_loaded[k], s_load);
 
         double* host_out = b.out;
@@ -733,12 +744,8 @@ void plan_compute(cuSten_t* h, bool offload)
     const MemKind kin = classify(h->dataInput[0]);
     const MemKind kout = classify(h->dataOutput[0]);
     MemKind kcoef = coef ? classify(coef) : MK_DEVICE;
-    if (s.weno && (kin == MK_HOST || kout == MK_HOST || classify(h->uVel[0]) == MK_HOST || classify(h->vVel[0]) == MK_HOST))
-    {
-        printf("\ncuSten: the WENO variant needs device or unified memory buffers (host staging is not implemented for it)\n"
-               "program terminated ...\n\n");
-        exit(EXIT_FAILURE);
-    }
+    // WENO: velocities in plain host memory send the call down the staged road like a host-resident field does
+    const bool weno_host_vel = s.weno && (classify(h->uVel[0]) == MK_HOST || classify(h->vVel[0]) == MK_HOST);
 
     // the previous call left work on all three streams: this one starts behind all of it
     if (p->spread) join_all(h, p);
@@ -766,7 +773,7 @@ void plan_compute(cuSten_t* h, bool offload)
         kcoef = MK_DEVICE;
     }
 
-    if (kin == MK_HOST || kout == MK_HOST) compute_staged(h, p, coef);
+    if (kin == MK_HOST || kout == MK_HOST || weno_host_vel) compute_staged(h, p, coef);
     else if (kin == MK_MANAGED || kout == MK_MANAGED) compute_managed(h, p, coef, kcoef, offload);
     else compute_resident(h, p, coef);
     p->joined_now = 0;

@@ -57,6 +57,7 @@ struct Plan
     // staging for host-resident grids
     double* d_in[kSlots];
     double* d_out[kSlots];
+    double* d_aux[kSlots];       // WENO variant: the tile's u rows followed by its v rows
     double* d_coef;
     size_t stage_rows;           // rows each d_in slot can hold
     cudaEvent_t ev_loaded[kSlots], ev_done[kSlots], ev_unloaded[kSlots];

@@ -35,11 +35,20 @@ def _ours(phi, u, v, dx, dy, tiles=1, kind="device", fallback=False):
         cs.cuStenCompute2DXYWENOADVp(h, cs.DEVICE)
         cs.device_synchronize()
         res = out.cpu().numpy()
+    elif kind == "pageable":
+        a = [np.ascontiguousarray(x, dtype=np.float64).copy() for x in (phi, u, v)]
+        res = np.zeros_like(a[0])
+        cs.cuStenCreate2DXYWENOADVp(h, 0, tiles, nx, ny, 32, 16, dx, dy, a[1].ctypes.data, a[2].ctypes.data, res.ctypes.data,
+                                    a[0].ctypes.data)
+        cs.cuStenCompute2DXYWENOADVp(h, cs.HOST)
+        cs.device_synchronize()
     else:
         import ctypes
         lib = cs.load()
         n = nx * ny
-        ptrs = [lib.custen_managed_alloc(n * 8) for _ in range(4)]
+        alloc, free = ((lib.custen_managed_alloc, lib.custen_managed_free) if kind == "managed"
+                       else (lib.custen_host_alloc, lib.custen_host_free))
+        ptrs = [alloc(n * 8) for _ in range(4)]
         views = [np.ctypeslib.as_array((ctypes.c_double * n).from_address(p)) for p in ptrs]
         for vw, a in zip(views[:3], (phi, u, v)):
             vw[:] = a.ravel()
@@ -50,9 +59,9 @@ def _ours(phi, u, v, dx, dy, tiles=1, kind="device", fallback=False):
         res = views[3].reshape(ny, nx).copy()
     path = cs.last_path(h)
     cs.cuStenDestroy2DXYWENOADVp(h)
-    if kind != "device":
+    if kind in ("managed", "pinned"):
         for p in ptrs:
-            lib.custen_managed_free(p)
+            free(p)
     cs.set_tuning()
     return res, path
 
@@ -69,6 +78,10 @@ def test_bit_exact_against_reference_weno_kernel(nx, ny, tiles):
     assert path == "fallback" and ol.count_diff(got_fb, ref) == 0
     got_m, _ = _ours(phi, u, v, dx, dy, tiles=tiles, kind="managed")
     assert ol.count_diff(got_m, ref) == 0
+    # host-resident fields and velocities: the staged out-of-core road (tile + halo rows + the tile's velocities per slot)
+    for kind in ("pinned", "pageable"):
+        got_h, _ = _ours(phi, u, v, dx, dy, tiles=tiles, kind=kind)
+        assert ol.count_diff(got_h, ref) == 0, kind
 
 
 def test_windows_outside_the_verified_powf_range_match_the_reference_kernel():
