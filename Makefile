@@ -1,5 +1,6 @@
 # cuSten-B200 build: sm_100a only.
-#   make lib      -> custen_b200/lib/libcuSten.a        (relocatable device code, the reference's library form)
+#   make lib      -> custen_b200/lib/libcuSten.a        (relocatable device code, the reference's library form; also
+#                                                        carries the additive C entry points of api_c.cu / slab.cu)
 #                    custen_b200/lib/libcusten_b200.so   (C ABI, device-linked, for FFI users and the tests)
 #   make oracle   -> oracle/_ref/*                       (CPU oracle + the reference rebuilt from /root/reference)
 NVCC      ?= nvcc
@@ -24,19 +25,27 @@ $(OBJDIR)/%.o: $(SRCDIR)/%.cu $(HEADERS)
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) -c -o $@ $<
 
-$(LIBDIR)/libcuSten.a: $(CORE_OBJ)
+# the archive = the reference's API + the additive C ABI and the multi-GPU slab layer (both only need the core), so that
+# a C++ program with its own __device__ functions can device-link custen_mg_* too (examples/multi_gpu_stencil.cu)
+ARCHIVE_OBJ := $(CORE_OBJ) $(OBJDIR)/api_c.o $(OBJDIR)/slab.o
+$(LIBDIR)/libcuSten.a: $(ARCHIVE_OBJ)
 	@mkdir -p $(LIBDIR)
-	$(NVCC) --lib $(CORE_OBJ) --output-file $@
+	rm -f $@
+	$(NVCC) --lib $(ARCHIVE_OBJ) --output-file $@
 
 $(LIBDIR)/libcusten_b200.so: $(CORE_OBJ) $(CABI_OBJ)
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(ARCH) -shared -o $@ $(CORE_OBJ) $(CABI_OBJ)
 
 # the re-hosted Cahn-Hilliard driver program (reference: cuPentSpeedUp/cuPentCahnADITiming)
-examples: examples/bin/cuPentCahnADI examples/bin/registered_fun
+examples: examples/bin/cuPentCahnADI examples/bin/registered_fun examples/bin/multi_gpu_stencil
 
 # a user program against the C++ drop-in API and the static archive, with a registered __device__ function
 examples/bin/registered_fun: examples/registered_fun.cu $(LIBDIR)/libcuSten.a $(HEADERS)
+	@mkdir -p examples/bin
+	$(NVCC) $(ARCH) -O3 -std=c++17 -rdc=true -o $@ $< $(LIBDIR)/libcuSten.a
+
+examples/bin/multi_gpu_stencil: examples/multi_gpu_stencil.cu $(LIBDIR)/libcuSten.a $(HEADERS)
 	@mkdir -p examples/bin
 	$(NVCC) $(ARCH) -O3 -std=c++17 -rdc=true -o $@ $< $(LIBDIR)/libcuSten.a
 

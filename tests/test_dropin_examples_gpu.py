@@ -50,6 +50,19 @@ def test_user_program_with_registered_function():
     assert "bit-identical" in r.stdout
 
 
+@pytest.mark.parametrize("n,steps,slabs", [(512, 7, 2), (1024, 10, 4), (2048, 5, 8)])
+def test_cpp_program_moves_its_time_stepper_to_slabs(n, steps, slabs):
+    """examples/multi_gpu_stencil.cu: a C++ translation unit with its own __device__ function, linked against libcuSten.a
+    only.  It time-steps a field with the reference API on one GPU, then runs the same steps through custen_mg_* on
+    y-slabs (over all GPUs of the box; several slabs share a GPU when there are fewer) and exits 0 iff no double differs."""
+    exe = os.path.join(ROOT, "examples", "bin", "multi_gpu_stencil")
+    if not os.path.exists(exe):
+        pytest.skip("examples not built (make examples)")
+    r = subprocess.run([exe, str(n), str(steps), str(slabs)], capture_output=True, text=True, timeout=180)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert " 0 of %d doubles differ" % (n * n) in r.stdout and "time-outs 0" in r.stdout
+
+
 @pytest.mark.parametrize("n,steps", [(512, 20), (4096, 3)])
 def test_reference_cahn_hilliard_driver_with_the_new_library(n, steps):
     """Zero-source-change proof for BASELINE config 5: the reference's GPU Cahn-Hilliard program (timing twin: driver,
