@@ -1,4 +1,11 @@
 mkdir -p gpurun_out
-examples/bin/multi_gpu_stencil 1024 10 2
-examples/bin/multi_gpu_stencil 4096 10 4
-timeout 900 python -m pytest tests/test_dropin_examples_gpu.py -q -m gpu -x 2>&1 | tail -3
+timeout 900 python -m pytest tests/test_cahn_gpu.py -q -m gpu -x -k "last_pass or steps_compose or graph_replay or switching or two_solvers" 2>&1 | tail -12
+for f in 1 0; do python - <<P
+import numpy as np, custen_b200 as cs
+from custen_b200.cahn import CahnHilliard
+cs.load().custen_cahn_set_fuse_new($f)
+for n in (4096, 2048, 512):
+    s = CahnHilliard(n, solver=2); s.set_field(np.random.default_rng(0).uniform(-0.1, 0.1, (n, n))); s.step(8)
+    print("fuse_new", $f, "n", n, "ms/step", [round(s.time_steps(40), 4) for _ in range(3)]); s.destroy()
+P
+done
