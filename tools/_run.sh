@@ -1,11 +1,13 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_cahn_gpu.py -q -m gpu -x -k "last_pass or steps_compose or graph_replay or switching or two_solvers" 2>&1 | tail -12
-for f in 1 0; do python - <<P
-import numpy as np, custen_b200 as cs
-from custen_b200.cahn import CahnHilliard
-cs.load().custen_cahn_set_fuse_new($f)
-for n in (4096, 2048, 512):
-    s = CahnHilliard(n, solver=2); s.set_field(np.random.default_rng(0).uniform(-0.1, 0.1, (n, n))); s.step(8)
-    print("fuse_new", $f, "n", n, "ms/step", [round(s.time_steps(40), 4) for _ in range(3)]); s.destroy()
+timeout 1500 python -m pytest tests -q -m gpu -x --durations=5 > gpurun_out/r2f_tests.log 2>&1; echo "rc=$?" >> gpurun_out/r2f_tests.log
+grep -n "^E   \|passed\|failed\|^FAILED\|rc=" gpurun_out/r2f_tests.log | cut -c1-250 | head -20
+timeout 900 python bench.py > gpurun_out/r2f_bench_n1.json 2> gpurun_out/r2f_bench_n1.err; echo "bench rc=$?"
+tail -c 300 gpurun_out/r2f_bench_n1.err
+python - <<'P'
+import json
+d=json.loads(open('gpurun_out/r2f_bench_n1.json').read().strip().splitlines()[-1])
+print(d['value'], d['ms_per_step'], d['roofline']['frac'], d['e2e']['value'], d['e2e']['link_frac'], d['clocks']['sm_mhz'], d['clocks']['reasons'])
+print({k:(v['gpoints_per_s'], v.get('opaque_pointer_gpoints_per_s'), v.get('example_fields_gpoints_per_s')) for k,v in d['variants_16384'].items()})
+print(d['cahn_hilliard_4096']['ms_per_step'], d['cahn_hilliard_512']['ms_per_step'])
 P
-done
+python -c "import __graft_entry__ as g; g.smoke()"

@@ -26,9 +26,9 @@ bench line's `clocks`, no thermal or hardware slow-down), FP64, grids device-res
 {peak:.0f} GB/s (`MEASURED_PEAKS.json`); algorithmic traffic 16 B/point (WENO: 32). Raw lines: `profiles/r2_bench_n*.json`;
 regenerate this section with `python tools/make_baseline_md.py`. Every `gpurun` call lands on a different B200 and the
 same kernel moves by a few per cent from box to box: the headline value (config 4, one GPU) came out at 372, 375, 388,
-393 and 395 Gpt/s over this round's runs; the tables below are from the last complete run at each GPU count (the
-single-GPU line predates the last change to the tile-family kernels, `profiles/r2_tile_carry_modes.log`, which added 4-5 %
-to XpFun / XnpFun and to XYpFun at 32768^2 on the box it was measured on).
+393, 395, 399 and 400 Gpt/s over this round's runs. The single-GPU tables are from the round's last run (final code);
+the 2-, 4- and 8-GPU lines were taken earlier in the round, before the last change to the tile-family kernels
+(`profiles/r2_tile_carry_modes.log`: +4-5 % for XpFun / XnpFun and for XYpFun at 32768^2), the "later box" line after it.
 
 ### 5.1 Every variant on 16384^2 (target: >= 80 % of HBM peak) - new engine vs the reference's own kernels on the same GPU
 
