@@ -20,15 +20,15 @@ def main():
     L.append(f"""
 ## 5. Measured on B200 (round 2)
 
-All numbers: B200 (148 SMs; SM clock under load 1900-1965 MHz, `sw_power_cap` reported on most boxes and kept in the
+All numbers: B200 (148 SMs; SM clock sampled under load 1530-1965 MHz, `sw_power_cap` reported on most boxes and kept in the
 bench line's `clocks`, no thermal or hardware slow-down), FP64, grids device-resident unless stated, CUDA-event timing
 (3 warm-ups, 10-20 timed sweeps, inputs far larger than L2). Roofline denominator: the driver's measured copy bandwidth
 {peak:.0f} GB/s (`MEASURED_PEAKS.json`); algorithmic traffic 16 B/point (WENO: 32). Raw lines: `profiles/r2_bench_n*.json`;
 regenerate this section with `python tools/make_baseline_md.py`. Every `gpurun` call lands on a different B200 and the
 same kernel moves by a few per cent from box to box: the headline value (config 4, one GPU) came out at 372, 375, 388,
-393, 395, 399 and 400 Gpt/s over this round's runs. The single-GPU tables are from the round's last run (final code);
-the 2-, 4- and 8-GPU lines were taken earlier in the round, before the last change to the tile-family kernels
-(`profiles/r2_tile_carry_modes.log`: +4-5 % for XpFun / XnpFun and for XYpFun at 32768^2), the "later box" line after it.
+393, 395, 399 and 400 Gpt/s over this round's runs. The 1- and 2-GPU lines are from the round's last runs (final code);
+the 4- and 8-GPU lines with `e2e` were taken earlier in the round, before the last change to the tile-family kernels
+(`profiles/r2_tile_carry_modes.log`: +4-5 % for XpFun / XnpFun and for XYpFun at 32768^2), the "later boxes" line after it.
 
 ### 5.1 Every variant on 16384^2 (target: >= 80 % of HBM peak) - new engine vs the reference's own kernels on the same GPU
 
@@ -84,9 +84,9 @@ unregistered user function; DESIGN.md 3.1 on why that road is callee-bound).
         he = d.get("halo_exchange") or {}
         L.append(f"| 4: same grid on {n} GPUs ({d['config']['parallelism']}, strong scaling) | **{d['value']:.0f} Gpt/s**, {d['ms_per_step']:.3f} ms/step, {100 * d['roofline']['frac']:.1f} % of HBM peak per GPU, {d['value'] / b['value']:.2f}x the single-GPU line above; parity: {d['parity']['rows_checked']} seam rows, {d['parity']['bits_differing']} differing bits, {d['parity']['neighbour_wait_timeouts']} wait time-outs"
                  + (f"; halo rows {he['bytes_received_per_gpu_per_sweep'] // 1024} KiB/GPU/sweep read over NVLink inside the sweep (the same rows as an NCCL send/recv exchange on their own: {he['nccl_exchange_us']} us)" if he else "") + " |")
-    late = {n: last_json(P(f"r2_bench_n{n}_late.json")) for n in (2, 4) if os.path.exists(P(f"r2_bench_n{n}_late.json"))}
+    late = {n: last_json(P(f"r2_bench_n{n}_late.json")) for n in (4, 8) if os.path.exists(P(f"r2_bench_n{n}_late.json"))}
     if late:
-        L.append("| 4: the same on a later box, final stencil kernels, `--no-e2e` | " + ", ".join(
+        L.append("| 4: the same on later boxes, final code, `--no-e2e` | " + ", ".join(
             f"{n} GPUs: {d['value']:.0f} Gpt/s = {100 * d['roofline']['frac']:.1f} % of HBM peak per GPU (SM clock under load {d['clocks']['sm_mhz']:.0f} MHz, {', '.join(d['clocks']['reasons']) or 'no throttle reason'})"
             for n, d in sorted(late.items())) + " |")
     e = b["e2e"]
