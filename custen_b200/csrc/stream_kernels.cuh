@@ -496,9 +496,10 @@ __global__ void __launch_bounds__(NT + 32, MINB) stream_acc_kernel(const __grid_
 
 // ---- stream_tile_kernel: a contiguous window in shared memory, handed to an operator --------------------------
 // One column per consumer thread (TW = NT): a warp reads consecutive 8-byte words, conflict free.  Each stage
-// buffer has PFX = V-1 rows in front of the rows the producer fills; after a stage is consumed its last V-1
-// rows are copied there for the next stage, so every window is contiguous with pitch PW and the user function
-// sees exactly the tile layout the reference gives it (data, loc, jump).
+// buffer has PFX = V-1 rows in front of the rows the producer fills; the last V-1 rows of the previous stage are
+// copied there (StreamArgs::warp_carry: by the producer warp once that stage has landed, or by all consumers behind a
+// block-wide barrier), so every window is contiguous with pitch PW and the user function sees exactly the tile layout
+// the reference gives it (data, loc, jump).
 
 struct OpWeights  // run-time H x V weights (shapes without a register-accumulator instance)
 {
